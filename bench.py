@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the nearest-cylinder label + offset path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] — a noise-augmented plot, 10M NoiseDataGeneration-style
+points against a 50k-cylinder QSM (10 synthetic trees), variant A (label generation).  One "step" labels the
+whole cloud once: device-resident fp32 points in, device-resident (index, id, distance, offset) out, including
+voxel binning, candidate-tile construction and the un-permuting write.  With N GPUs every rank labels its own
+10M-point cloud against the same table, which rank 0 broadcasts once over NCCL (weak scaling, no data-path
+collective).  Prints ONE JSON line on rank 0.
+
+Timing: CUDA events on the launching stream around every step, L2 flushed between steps (256 MiB write),
+barrier + synchronize on both sides of the timed loop, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 10_000_000
+N_CYLINDERS = 50_000
+METRIC = "points/sec nearest-cylinder label+offset"
+UNIT = "points/s"
+OPS_PER_PAIR = 81                 # fp32 lane-ops per evaluated pair in reference order
+BYTES_PER_POINT = 36              # compulsory HBM traffic per point: 12 B xyz in + 24 B index/id/dist/offset out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thread, self.gpu = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 <= ts <= t1 + 0.2:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:                           # timed region shorter than the sampling period: take the nearest samples
+            sm = [float(l.split(",")[1]) for _, l in self.rows[-3:] if l.count(",") >= 8]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(seed_points: int):
+    from treemorph_b200 import synth
+    qsm = synth.random_qsm(N_CYLINDERS, seed=1)
+    pts = synth.sample_points(qsm, N_POINTS, seed=seed_points)
+    return qsm, pts
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host cores (oracle port; the reference is Python/torch and
+# does not travel to the GPU box)
+# ------------------------------------------------------------------------------------------------------------
+
+def cpu_sample_size(target_s: float, qsm, pts, variant) -> tuple[int, float]:
+    """Calibrate on 2k points, then size the sample for ~target_s seconds of CPU work."""
+    from oracle import oracle
+    from treemorph_b200 import synth
+    arrs = synth.cylinder_arrays(qsm, variant.axis_eps)
+    t0 = time.perf_counter()
+    oracle.label(pts[:2000], *_oracle_args(arrs), variant)
+    dt = time.perf_counter() - t0
+    n = int(min(len(pts), max(2000, 2000 * target_s / max(dt, 1e-4))))
+    return n, dt
+
+
+def _oracle_args(arrs):
+    start, radius, length, unit, ids = arrs
+    return start, radius, length, unit, ids
+
+
+def run_cpu(qsm, pts, n_sample: int, threads: int = 0):
+    from oracle import oracle
+    from treemorph_b200 import synth
+    arrs = synth.cylinder_arrays(qsm)
+    t0 = time.perf_counter()
+    res = oracle.label(pts[:n_sample], *_oracle_args(arrs), oracle.VARIANT_A, threads=threads)
+    return time.perf_counter() - t0, res
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+    oracle.build()
+    qsm, pts = build_workload(2)
+    n_s, _ = cpu_sample_size(4.0, qsm, pts, oracle.VARIANT_A)
+    for _ in range(args.warmup):
+        run_cpu(qsm, pts, min(n_s, 4000))
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = run_cpu(qsm, pts, n_s)
+        total += dt
+    value = n_s * args.steps / total
+    cores = oracle.max_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{N_POINTS} points x {N_CYLINDERS} cylinders, variant A (label generation)",
+                   "sample": f"first {n_s} points of the cloud against all {N_CYLINDERS} cylinders per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_s} points x {N_CYLINDERS} cylinders per step, {args.steps} steps, OpenMP {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------------
+
+def main():
+    global N_POINTS, N_CYLINDERS
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="grid", choices=["grid", "brute", "auto"])
+    ap.add_argument("--cell", type=float, default=0.0)
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--cylinders", type=int, default=N_CYLINDERS)
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-brute", action="store_true", help="skip the exhaustive-kernel FP32 yard-stick")
+    args = ap.parse_args()
+    N_POINTS, N_CYLINDERS = args.points, args.cylinders
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this path has no CPU fallback"}))
+        return 1
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from treemorph_b200 import api, sharding, synth
+    eng = api.Engine(dev)
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+
+    # ---- inputs: rank 0 owns the QSM and broadcasts the packed table once; every rank samples its own cloud
+    t_gen = time.time()
+    qsm = synth.random_qsm(N_CYLINDERS, seed=1)
+    table = None
+    if rank == 0:
+        start, radius, length, unit, ids = synth.cylinder_arrays(qsm)
+        table = sharding.pack_table(torch.tensor(start), torch.tensor(radius), torch.tensor(length), torch.tensor(unit),
+                                    torch.tensor(ids)).to(dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    table = sharding.broadcast_table(table, dev)
+    e1.record()
+    torch.cuda.synchronize()
+    bcast_ms = e0.elapsed_time(e1)
+    s_t, r_t, l_t, u_t, i_t = sharding.unpack_table(table)
+    pts_host = synth.sample_points(qsm, N_POINTS, seed=2 + rank)
+    pinned_in = torch.empty((N_POINTS, 3), dtype=torch.float32, pin_memory=True)
+    pinned_in.numpy()[:] = pts_host
+    dpts = pinned_in.to(dev, non_blocking=True)
+    out = {"index": torch.empty(N_POINTS, dtype=torch.int32, device=dev), "id": torch.empty(N_POINTS, dtype=torch.int32, device=dev),
+           "dist": torch.empty(N_POINTS, dtype=torch.float32, device=dev),
+           "offset": torch.empty((N_POINTS, 3), dtype=torch.float32, device=dev)}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t_gen
+
+    # ---- table install (per QSM, not per step): pack + solid AABBs + voxel index
+    e0.record()
+    eng.set_cylinders(s_t, r_t, l_t, u_t, i_t)
+    eng.label(dpts[:4096], api.VARIANT_A, mode=args.mode, cell_size=args.cell, want=("id",))     # builds the voxel index
+    e1.record()
+    torch.cuda.synchronize()
+    setup_ms = e0.elapsed_time(e1)
+
+    def step():
+        eng.label(dpts, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=out, want=("index", "id", "dist", "offset"))
+
+    for _ in range(warmup):
+        flush.fill_(1)
+        step()
+    torch.cuda.synchronize()
+    stats = eng.stats()
+
+    # ---- timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for a, b in evs:
+        flush.fill_(1)                      # evict the previous step's working set from the 126 MB L2
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+    ms_per_step = total_ms / steps
+    value = world * N_POINTS * steps / (total_ms * 1e-3)
+
+    # ---- per-phase device time of the dominant kernel (CUDA events inside the library, same stream)
+    eng.set_profiling(True)
+    phase_acc = {}
+    for _ in range(3):
+        flush.fill_(1)
+        step()
+        for k, v in eng.phase_ms().items():
+            phase_acc.setdefault(k, []).append(v)
+    eng.set_profiling(False)
+    phases = {k: float(np.mean(v)) for k, v in phase_acc.items()}
+    stats = eng.stats()
+
+    # ---- end to end through the public host API: pinned host cloud in, pinned (N,7) float64 records out
+    rec_pinned = torch.empty((N_POINTS, 7), dtype=torch.float64, pin_memory=True)
+    rec_np, cloud_np = rec_pinned.numpy(), pinned_in.numpy()
+    e2e_steps = max(2, min(steps, 5))
+    for _ in range(2):
+        eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_POINTS * e2e_steps / float(te.item())
+    e2e_ok = bool((rec_np[:1000, 6] == out["id"][:1000].cpu().numpy()).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- rooflines
+    hbm_peak, peak_kind = load_peaks()
+    fp32_peak = eng.fp32_peak()
+    dom = max(("evaluate", "exhaustive", "bin", "scatter", "tile_build", "scan"), key=lambda k: phases.get(k, 0.0))
+    dom_ms = phases.get(dom, 0.0) or ms_per_step
+    achieved_gbs = BYTES_PER_POINT * N_POINTS / (dom_ms * 1e-3) / 1e9
+    pairs = stats["pairs_evaluated"]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "kernel_ms": dom_ms,
+                "note": "dominant kernel is FP32-issue bound, not HBM bound: see fp32_roofline"}
+    fp32_roofline = {"kernel": dom, "pairs_evaluated": pairs, "lane_ops_per_pair": OPS_PER_PAIR,
+                     "achieved_lane_ops_per_s": pairs * OPS_PER_PAIR / (dom_ms * 1e-3), "peak_lane_ops_per_s": fp32_peak,
+                     "frac": pairs * OPS_PER_PAIR / (dom_ms * 1e-3) / fp32_peak if fp32_peak else None,
+                     "peak_source": "FFMA/FADD+FMUL chain probe in this run"}
+
+    # ---- exhaustive kernel as the FP32 yard-stick (pairs = N*M exactly)
+    brute = None
+    if not args.skip_brute:
+        nb = min(N_POINTS, 400_000)
+        eng.label(dpts[:nb], api.VARIANT_A, mode="brute", want=("id",))
+        torch.cuda.synchronize()
+        e0.record()
+        eng.label(dpts[:nb], api.VARIANT_A, mode="brute", want=("index", "id", "dist", "offset"))
+        e1.record()
+        torch.cuda.synchronize()
+        bms = e0.elapsed_time(e1)
+        bp = nb * N_CYLINDERS
+        brute = {"points": nb, "pairs": bp, "ms": bms, "pairs_per_s": bp / (bms * 1e-3),
+                 "fp32_frac": bp * OPS_PER_PAIR / (bms * 1e-3) / fp32_peak if fp32_peak else None}
+
+    # ---- reference algorithm on the host cores, bounded sample, same run
+    cpu = None
+    if not args.skip_cpu:
+        from oracle import oracle
+        oracle.build()
+        n_s, _ = cpu_sample_size(12.0, qsm, pts_host, oracle.VARIANT_A)
+        dt, res = run_cpu(qsm, pts_host, n_s)
+        same = bool((res["id"] == out["id"][:n_s].cpu().numpy()).all())
+        cpu = {"value": n_s / dt, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
+               "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {oracle.max_threads()} threads "
+                         f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
+
+    launches_per_step = {"grid": 9, "auto": 9, "brute": 2}[args.mode]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{N_POINTS} points x {N_CYLINDERS} cylinders per GPU, variant A (label generation), "
+                               f"random QSM plot + NoiseDataGeneration-style cloud", "mode": args.mode,
+                   "cell_size_m": stats.get("cell_size"), "l2": "flushed between steps (256 MiB write)",
+                   "parallelism": f"points sharded x{world}, cylinder table broadcast once"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * 12, "d2h_bytes_per_step": N_POINTS * 56,
+                "api": "Engine.label_cloud_host (tm_label_cloud_host): pinned fp32 cloud -> pinned (N,7) float64 records",
+                "steps": e2e_steps, "checked": e2e_ok},
+        "gpu_launches": launches_per_step * steps,
+        "roofline": roofline, "fp32_roofline": fp32_roofline, "brute_force_yardstick": brute,
+        "cpu_baseline": cpu,
+        "phases_ms": phases, "stats": stats, "setup_ms": setup_ms, "table_broadcast_ms": bcast_ms,
+        "input_generation_s": gen_s,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

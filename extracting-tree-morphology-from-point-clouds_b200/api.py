@@ -1,0 +1,244 @@
+"""Device-level Python API over the C-ABI library: torch tensors in, torch tensors out.
+
+torch is used for device memory and streams only; every computation happens in
+``libtreemorph_nn.so`` (hand-written sm_100a CUDA).  The functions here mirror the reference's
+argument conventions for the hot path:
+
+* ``closest_cylinder_cuda_batch(points, start, radius, axis_length, axis_unit, IDs, device)``
+  (``PreProcessing/LabelGenerationCuda.py:20``, ``Modules/Projection.py:19``)  → ``Engine.label``
+* the cylinder preparation of ``generate_offset_cloud_cuda_batched`` (``LabelGenerationCuda.py:117-123``,
+  ``Projection.py:121-132``) → ``Engine.prepare``
+* the ``(N,7)`` float64 record (``LabelGenerationCuda.py:114,131-133``) → ``Engine.assemble`` /
+  ``Engine.label_cloud_host``
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import binding as B
+
+
+@dataclass(frozen=True)
+class Variant:
+    """The two parameterisations of the reference kernel."""
+    name: str
+    perp_atol: float      # LabelGenerationCuda.py:51 (1e-6)  /  Projection.py:50 (1e-3)
+    norm_eps: float       # Projection.py:60-62 (1e-8); 0 = unguarded (LabelGenerationCuda.py:58-60)
+    axis_eps: float       # Projection.py:129-131 (1e-8); 0 = unguarded (LabelGenerationCuda.py:123)
+
+
+VARIANT_A = Variant("A", 1e-6, 0.0, 0.0)       # PreProcessing/LabelGenerationCuda.py
+VARIANT_B = Variant("B", 1e-3, 1e-8, 1e-8)     # Modules/Projection.py
+VARIANTS = {"A": VARIANT_A, "B": VARIANT_B}
+MODES = {"auto": B.TM_MODE_AUTO, "brute": B.TM_MODE_BRUTE, "grid": B.TM_MODE_GRID}
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("treemorph_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else int(t.data_ptr())
+
+
+class Engine:
+    """One C-ABI handle (one device, one host thread)."""
+
+    def __init__(self, device: torch.device | int | str | None = None):
+        _require_cuda()
+        self._lib = B.load()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError(f"Engine needs a cuda device, got {dev}")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        h = ctypes.c_void_p()
+        B.check(self._lib, None, self._lib.tm_create(dev.index, ctypes.byref(h)))
+        self._h = h
+        self.m = 0
+        self._keep: tuple = ()
+
+    # -- lifetime ----------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.tm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status: int) -> None:
+        B.check(self._lib, self._h, status)
+
+    def _f32(self, t, cols: int | None = None) -> torch.Tensor:
+        t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != torch.float32:
+            t = t.to(device=self.device, dtype=torch.float32)
+        if cols is not None and (t.dim() != 2 or t.shape[1] != cols):
+            raise ValueError(f"expected a (M,{cols}) tensor, got {tuple(t.shape)}")
+        return t
+
+    # -- cylinder side -----------------------------------------------------------------------
+    def prepare(self, start, end, variant: Variant = VARIANT_A, norm_fma: bool = False):
+        """``axis_length`` (M,1) and ``axis_unit`` (M,3) as generate_offset_cloud_cuda_batched builds them."""
+        start = self._f32(start, 3)
+        end = self._f32(end, 3)
+        m = start.shape[0]
+        length = torch.empty((m, 1), dtype=torch.float32, device=self.device)
+        unit = torch.empty((m, 3), dtype=torch.float32, device=self.device)
+        self._check(self._lib.tm_prepare_cylinders(
+            self._h, _ptr(start), start.stride(0), start.stride(1), _ptr(end), end.stride(0), end.stride(1), m,
+            float(variant.axis_eps), int(bool(norm_fma)), _ptr(length), _ptr(unit), _stream_ptr(self.device)))
+        return length, unit
+
+    def set_cylinders(self, start, radius, axis_length, axis_unit, ids=None) -> None:
+        """Install the cylinder table (any strides; Fortran-ordered DataFrame tensors are read in place)."""
+        start = self._f32(start, 3)
+        unit = self._f32(axis_unit, 3)
+        m = start.shape[0]
+        length = self._f32(axis_length).reshape(-1)
+        radius = self._f32(radius).reshape(-1)
+        if unit.shape[0] != m or length.numel() != m or radius.numel() != m:
+            raise ValueError("cylinder arrays disagree on M")
+        if ids is not None:
+            ids = torch.as_tensor(ids)
+            if ids.device != self.device or ids.dtype != torch.int32:
+                ids = ids.to(device=self.device, dtype=torch.int32)
+            ids = ids.reshape(-1)
+            if ids.numel() != m:
+                raise ValueError("IDs disagree on M")
+        self._check(self._lib.tm_set_cylinders(
+            self._h, _ptr(start), start.stride(0), start.stride(1), _ptr(unit), unit.stride(0), unit.stride(1),
+            _ptr(length), length.stride(0) if m else 1, _ptr(radius), radius.stride(0) if m else 1,
+            _ptr(ids), (ids.stride(0) if m else 1) if ids is not None else 1, m, _stream_ptr(self.device)))
+        self.m = m
+
+    # -- point side --------------------------------------------------------------------------
+    def _params(self, variant: Variant, move_to_mantle: bool, norm_fma: bool, mode: str, cell_size: float) -> B.TmParams:
+        p = B.TmParams()
+        p.perp_atol = float(variant.perp_atol)
+        p.norm_eps = float(variant.norm_eps)
+        p.move_to_mantle = int(bool(move_to_mantle))
+        p.norm_fma = int(bool(norm_fma))
+        p.mode = MODES[mode]
+        p.cell_size = float(cell_size)
+        return p
+
+    def label(self, points: torch.Tensor, variant: Variant = VARIANT_A, move_to_mantle: bool = True,
+              norm_fma: bool = False, mode: str = "auto", cell_size: float = 0.0,
+              want=("index", "id", "dist", "offset"), out: dict | None = None) -> dict:
+        """closest_cylinder_cuda_batch for device-resident points → dict of device tensors."""
+        if points.device != self.device or points.dtype != torch.float32:
+            points = points.to(device=self.device, dtype=torch.float32)
+        if points.dim() != 2 or points.shape[1] < 3:
+            raise ValueError(f"points must be (N, >=3), got {tuple(points.shape)}")
+        if points.shape[0] > 1 and points.stride(1) != 1:
+            points = points.contiguous()
+        n = points.shape[0]
+        row_stride = points.stride(0) if n > 1 else max(3, points.shape[1])
+        shapes = {"index": ((n,), torch.int32), "id": ((n,), torch.int32), "dist": ((n,), torch.float32),
+                  "offset": ((n, 3), torch.float32), "radius": ((n,), torch.float32)}
+        res = {}
+        for k in want:
+            if out is not None and k in out:
+                t = out[k]
+                if t.shape != shapes[k][0] or t.dtype != shapes[k][1] or not t.is_contiguous() or t.device != self.device:
+                    raise ValueError(f"out[{k!r}] has the wrong shape / dtype / device")
+                res[k] = t
+            else:
+                res[k] = torch.empty(shapes[k][0], dtype=shapes[k][1], device=self.device)
+        prm = self._params(variant, move_to_mantle, norm_fma, mode, cell_size)
+        self._check(self._lib.tm_label_points(
+            self._h, _ptr(points), n, row_stride, ctypes.byref(prm), _ptr(res.get("index")), _ptr(res.get("id")),
+            _ptr(res.get("dist")), _ptr(res.get("offset")), _ptr(res.get("radius")), _stream_ptr(self.device)))
+        return res
+
+    def assemble(self, cloud: torch.Tensor, offset: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+        """(N,7) float64 [xyz, offset, ID] on the device; xyz keeps the cloud's own precision."""
+        if cloud.dtype not in (torch.float32, torch.float64):
+            cloud = cloud.to(torch.float64)
+        if cloud.device != self.device:
+            cloud = cloud.to(self.device)
+        if cloud.shape[0] > 1 and cloud.stride(1) != 1:
+            cloud = cloud.contiguous()
+        n = cloud.shape[0]
+        out = torch.empty((n, 7), dtype=torch.float64, device=self.device)
+        self._check(self._lib.tm_assemble_records(
+            self._h, _ptr(cloud), B.TM_F32 if cloud.dtype == torch.float32 else B.TM_F64, n,
+            cloud.stride(0) if n > 1 else max(3, cloud.shape[1]), _ptr(offset.contiguous()), _ptr(ids.contiguous()),
+            _ptr(out), _stream_ptr(self.device)))
+        return out
+
+    def label_cloud_host(self, cloud: np.ndarray, variant: Variant = VARIANT_A, move_to_mantle: bool = True,
+                         norm_fma: bool = False, mode: str = "auto", cell_size: float = 0.0,
+                         out: np.ndarray | None = None, want_dist: bool = False):
+        """generate_offset_cloud_cuda_batched for a host cloud: pipelined H2D / label / assemble / D2H."""
+        cloud = np.asarray(cloud)
+        if cloud.ndim != 2 or cloud.shape[1] < 3:
+            raise ValueError(f"cloud must be (N, >=3), got {cloud.shape}")
+        if cloud.dtype not in (np.float32, np.float64):
+            cloud = cloud.astype(np.float64)
+        if cloud.shape[0] > 1 and (cloud.strides[1] != cloud.itemsize or cloud.strides[0] % cloud.itemsize
+                                   or cloud.strides[0] < 3 * cloud.itemsize):
+            cloud = np.ascontiguousarray(cloud)
+        n = cloud.shape[0]
+        if out is None:
+            out = np.empty((n, 7), dtype=np.float64)
+        if out.shape != (n, 7) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 (N,7) array")
+        dist = np.empty(n, dtype=np.float32) if want_dist else None
+        prm = self._params(variant, move_to_mantle, norm_fma, mode, cell_size)
+        row_stride = cloud.strides[0] // cloud.itemsize if n > 1 else max(3, cloud.shape[1])
+        self._check(self._lib.tm_label_cloud_host(
+            self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride,
+            ctypes.byref(prm), out.ctypes.data, dist.ctypes.data if dist is not None else None))
+        return (out, dist) if want_dist else out
+
+    # -- introspection -----------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = B.TmStats()
+        self._check(self._lib.tm_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def set_profiling(self, enabled: bool) -> None:
+        self._check(self._lib.tm_set_profiling(self._h, int(bool(enabled))))
+
+    def phase_ms(self) -> dict:
+        """Device time of each phase of the last ``label`` call (needs ``set_profiling(True)``)."""
+        buf = (ctypes.c_float * B.TM_PHASES)()
+        self._check(self._lib.tm_get_phase_ms(self._h, buf))
+        return dict(zip(B.PHASE_NAMES, (float(v) for v in buf)))
+
+    def fp32_peak(self) -> float:
+        """Measured FP32 lane-operations per second of this GPU (FFMA / FADD+FMUL chains)."""
+        v = ctypes.c_double()
+        self._check(self._lib.tm_measure_fp32_peak(self._h, ctypes.byref(v)))
+        return float(v.value)
+
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: torch.device | int | str | None = None) -> Engine:
+    """Process-wide engine per device (the drop-in modules share it)."""
+    _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    eng = _engines.get(idx)
+    if eng is None or eng._h is None:
+        eng = Engine(torch.device("cuda", idx))
+        _engines[idx] = eng
+    return eng

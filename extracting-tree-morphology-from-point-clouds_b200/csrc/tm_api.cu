@@ -1,0 +1,522 @@
+// C ABI of the library (include/treemorph_nn.h): handle management, cylinder preparation and
+// packing, dispatch between the exhaustive and voxel-grid kernels, record assembly and the
+// pipelined host entry point.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <new>
+
+#include "tm_core.cuh"
+#include "tm_eval.cuh"
+
+namespace tmn {
+
+// ------------------------------------------------------------------------------------------------
+// cylinder preparation: LabelGenerationCuda.py:121-123 / Projection.py:126-132
+// ------------------------------------------------------------------------------------------------
+template <bool NFMA>
+__global__ void prepare_kernel(const float *__restrict__ start, int64_t s_rs, int64_t s_cs, const float *__restrict__ end,
+                               int64_t e_rs, int64_t e_cs, int64_t m, float axis_eps, float *__restrict__ out_len,
+                               float *__restrict__ out_unit) {
+    const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (c >= m) return;
+    // axis = end - start
+    const float ax = sub(end[c * e_rs], start[c * s_rs]);
+    const float ay = sub(end[c * e_rs + e_cs], start[c * s_rs + s_cs]);
+    const float az = sub(end[c * e_rs + 2 * e_cs], start[c * s_rs + 2 * s_cs]);
+    // axis_length = torch.norm(axis, dim=1, keepdim=True)
+    const float len = norm3<NFMA>(ax, ay, az);
+    // Projection.py:129-131: safe_axis_length[safe_axis_length < eps] = eps   (variant A: no guard)
+    const float dv = (axis_eps > 0.f && len < axis_eps) ? axis_eps : len;
+    out_len[c] = len;                       // the UNguarded length is what the kernel receives (Projection.py:137)
+    out_unit[3 * c] = __fdiv_rn(ax, dv);
+    out_unit[3 * c + 1] = __fdiv_rn(ay, dv);
+    out_unit[3 * c + 2] = __fdiv_rn(az, dv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cylinder table packing
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+
+// One thread per cylinder: two float4 records, the solid-cylinder AABB, and the classification
+//   regular : finite, unit (or zero) axis  → participates in the voxel index
+//   special : anything else (NaN axis of a zero-length cylinder in variant A, ...) → cannot be
+//             pruned, evaluated for every point
+__global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64_t s_cs, const float *__restrict__ unit,
+                            int64_t u_rs, int64_t u_cs, const float *__restrict__ length, int64_t l_s,
+                            const float *__restrict__ radius, int64_t r_s, const int32_t *__restrict__ ids, int64_t i_s,
+                            int m, float4 *__restrict__ recA, float4 *__restrict__ recB, int32_t *__restrict__ out_ids,
+                            float4 *__restrict__ boxlo, float4 *__restrict__ boxhi, int *__restrict__ bbox,
+                            int32_t *__restrict__ special) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const float sx = start[c * s_rs], sy = start[c * s_rs + s_cs], sz = start[c * s_rs + 2 * s_cs];
+    const float ux = unit[c * u_rs], uy = unit[c * u_rs + u_cs], uz = unit[c * u_rs + 2 * u_cs];
+    const float len = length[c * l_s], rad = radius[c * r_s];
+    recA[c] = make_float4(sx, sy, sz, len);
+    recB[c] = make_float4(ux, uy, uz, rad);
+    out_ids[c] = ids ? ids[c * i_s] : c;
+    const bool finite = isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(ux) && isfinite(uy) && isfinite(uz) &&
+                        isfinite(len) && isfinite(rad);
+    const float un = ux * ux + uy * uy + uz * uz;
+    const bool unit_ok = fabsf(un - 1.f) <= 1e-3f || (un == 0.f && len == 0.f);
+    if (!finite || !unit_ok || len < 0.f) {
+        boxlo[c] = make_float4(0.f, 0.f, 0.f, 1.f);
+        boxhi[c] = make_float4(0.f, 0.f, 0.f, 1.f);
+        const int s = atomicAdd(&bbox[6], 1);
+        special[s] = c;
+        return;
+    }
+    const float ex = fmaf(len, ux, sx), ey = fmaf(len, uy, sy), ez = fmaf(len, uz, sz);
+    const float ar = fabsf(rad);
+    float lx = fminf(sx, ex) - ar, ly = fminf(sy, ey) - ar, lz = fminf(sz, ez) - ar;
+    float hx = fmaxf(sx, ex) + ar, hy = fmaxf(sy, ey) + ar, hz = fmaxf(sz, ez) + ar;
+    const float px = 1e-6f * fmaxf(fabsf(lx), fabsf(hx)) + 1e-6f;
+    const float py = 1e-6f * fmaxf(fabsf(ly), fabsf(hy)) + 1e-6f;
+    const float pz = 1e-6f * fmaxf(fabsf(lz), fabsf(hz)) + 1e-6f;
+    lx -= px; ly -= py; lz -= pz; hx += px; hy += py; hz += pz;
+    boxlo[c] = make_float4(lx, ly, lz, 0.f);
+    boxhi[c] = make_float4(hx, hy, hz, 0.f);
+    atomicMin(&bbox[0], float_to_ordered(lx)); atomicMin(&bbox[1], float_to_ordered(ly)); atomicMin(&bbox[2], float_to_ordered(lz));
+    atomicMax(&bbox[3], float_to_ordered(hx)); atomicMax(&bbox[4], float_to_ordered(hy)); atomicMax(&bbox[5], float_to_ordered(hz));
+    atomicAdd(&bbox[7], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (N,7) float64 record of generate_offset_cloud_cuda_batched (LabelGenerationCuda.py:114,131-133)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void assemble_kernel(const T *__restrict__ cloud, int64_t n, int64_t row_stride, const float *__restrict__ offset,
+                                const int32_t *__restrict__ id, double *__restrict__ out) {
+    // 7 consecutive threads write one row → fully coalesced 8-byte stores
+    const int64_t total = n * 7;
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = e / 7;
+        const int col = static_cast<int>(e - row * 7);
+        double v;
+        if (col < 3) v = static_cast<double>(cloud[row * row_stride + col]);       // xyz at the caller's precision
+        else if (col < 6) v = static_cast<double>(offset[3 * row + (col - 3)]);
+        else v = static_cast<double>(id[row]);
+        out[e] = v;
+    }
+}
+
+__global__ void f64_to_f32_xyz_kernel(const double *__restrict__ cloud, int64_t n, int64_t row_stride, float *__restrict__ out) {
+    const int64_t total = n * 3;
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = e / 3;
+        const int col = static_cast<int>(e - row * 3);
+        out[e] = static_cast<float>(cloud[row * row_stride + col]);               // torch.tensor(points, dtype=float32): RNE
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 pipe probe
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float *out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+        if (KIND == 0) {            // FFMA, register operands
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        } else {                    // alternating FMUL / FADD, the instruction mix of the distance kernel
+            x0 = __fmul_rn(x0, a); x1 = __fadd_rn(x1, b); x2 = __fmul_rn(x2, a); x3 = __fadd_rn(x3, b);
+            x4 = __fmul_rn(x4, a); x5 = __fadd_rn(x5, b); x6 = __fmul_rn(x6, a); x7 = __fadd_rn(x7, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;   // never true in practice; keeps the chains alive
+}
+
+}  // namespace tmn
+
+using namespace tmn;
+
+extern "C" {
+
+int tm_version(void) { return TM_ABI_VERSION; }
+
+const char *tm_status_string(int status) {
+    switch (status) {
+        case TM_OK: return "ok";
+        case TM_ERR_INVALID: return "invalid argument";
+        case TM_ERR_NO_CYLINDERS: return "argmin(): expected reduction dim 1 to have non-zero size (no cylinders)";
+        case TM_ERR_CUDA: return "CUDA error";
+        case TM_ERR_NOMEM: return "out of memory";
+        case TM_ERR_STATE: return "call order violated";
+        default: return "unknown status";
+    }
+}
+
+const char *tm_last_error(const tm_handle *h) { return h ? h->err : "null handle"; }
+
+int tm_create(int device, tm_handle **out) {
+    if (!out) return TM_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return TM_ERR_CUDA;
+    tm_handle *h = new (std::nothrow) tm_handle();
+    if (!h) return TM_ERR_NOMEM;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return TM_ERR_CUDA; }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
+    *out = h;
+    return TM_OK;
+}
+
+int tm_destroy(tm_handle *h) {
+    if (!h) return TM_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_list,
+                          &h->long_list, &h->special, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count, &h->cell_start,
+                          &h->block_sums, &h->sorted_pts, &h->occ_cells, &h->tile_meta, &h->tileA, &h->tileB, &h->tileI,
+                          &h->items, &h->outlier_idx, &h->dstats, &h->scratch_f};
+    for (auto *b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        h->chunk_in[i].release(); h->chunk_rec[i].release(); h->chunk_off[i].release(); h->chunk_id[i].release();
+        h->chunk_dist[i].release();
+        if (h->pinned_in[i]) cudaFreeHost(h->pinned_in[i]);
+        if (h->pinned_out[i]) cudaFreeHost(h->pinned_out[i]);
+    }
+    for (auto &s : h->pipe_stream) if (s) cudaStreamDestroy(s);
+    for (auto &e : h->pipe_event) if (e) cudaEventDestroy(e);
+    for (auto &e : h->phase_ev) if (e) cudaEventDestroy(e);
+    delete h;
+    return TM_OK;
+}
+
+int tm_prepare_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_cs, const float *end, int64_t e_rs,
+                         int64_t e_cs, int64_t m, float axis_eps, int32_t norm_fma, float *out_len, float *out_unit,
+                         void *stream) {
+    if (!h) return TM_ERR_INVALID;
+    if (m < 0 || (m > 0 && (!start || !end || !out_len || !out_unit)))
+        return fail(h, TM_ERR_INVALID, "tm_prepare_cylinders: null pointer or negative size%s%s");
+    if (m == 0) return TM_OK;
+    TM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = static_cast<int>((m + 127) / 128);
+    if (norm_fma) prepare_kernel<true><<<blocks, 128, 0, st>>>(start, s_rs, s_cs, end, e_rs, e_cs, m, axis_eps, out_len, out_unit);
+    else prepare_kernel<false><<<blocks, 128, 0, st>>>(start, s_rs, s_cs, end, e_rs, e_cs, m, axis_eps, out_len, out_unit);
+    TM_CUDA(h, cudaGetLastError());
+    return TM_OK;
+}
+
+int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_cs, const float *unit, int64_t u_rs, int64_t u_cs,
+                     const float *length, int64_t l_s, const float *radius, int64_t r_s, const int32_t *ids, int64_t i_s,
+                     int64_t m, void *stream) {
+    if (!h) return TM_ERR_INVALID;
+    if (m < 0 || m > 0x7ffffff0LL) return fail(h, TM_ERR_INVALID, "tm_set_cylinders: cylinder count out of range%s%s");
+    if (m > 0 && (!start || !unit || !length || !radius))
+        return fail(h, TM_ERR_INVALID, "tm_set_cylinders: null cylinder array%s%s");
+    TM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->m = m;
+    h->have_cyl = true;
+    h->have_grid = false;
+    h->n_special = h->n_long = h->n_listed = 0;
+    if (m == 0) return TM_OK;
+    const size_t mm = static_cast<size_t>(m);
+    TM_CUDA(h, h->recA.ensure(sizeof(float4) * mm));
+    TM_CUDA(h, h->recB.ensure(sizeof(float4) * mm));
+    TM_CUDA(h, h->ids.ensure(sizeof(int32_t) * mm));
+    TM_CUDA(h, h->boxlo.ensure(sizeof(float4) * mm));
+    TM_CUDA(h, h->boxhi.ensure(sizeof(float4) * mm));
+    TM_CUDA(h, h->special.ensure(sizeof(int32_t) * mm));
+    TM_CUDA(h, h->bbox.ensure(sizeof(int) * 8));
+    const int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, static_cast<int>(0x80000000), static_cast<int>(0x80000000),
+                         static_cast<int>(0x80000000), 0, 0};
+    TM_CUDA(h, cudaMemcpyAsync(h->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int blocks = static_cast<int>((m + 127) / 128);
+    pack_kernel<<<blocks, 128, 0, st>>>(start, s_rs, s_cs, unit, u_rs, u_cs, length, l_s, radius, r_s, ids, i_s,
+                                        static_cast<int>(m), h->recA.as<float4>(), h->recB.as<float4>(), h->ids.as<int32_t>(),
+                                        h->boxlo.as<float4>(), h->boxhi.as<float4>(), h->bbox.as<int>(),
+                                        h->special.as<int32_t>());
+    TM_CUDA(h, cudaGetLastError());
+    TM_CUDA(h, cudaStreamSynchronize(st));      // `init` is a stack buffer; also surfaces bad input pointers here
+    return TM_OK;
+}
+
+static int check_params(tm_handle *h, const tm_params *p) {
+    if (!p) return fail(h, TM_ERR_INVALID, "null tm_params%s%s");
+    if (p->mode != TM_MODE_AUTO && p->mode != TM_MODE_BRUTE && p->mode != TM_MODE_GRID)
+        return fail(h, TM_ERR_INVALID, "tm_params.mode must be TM_MODE_AUTO, TM_MODE_BRUTE or TM_MODE_GRID%s%s");
+    if (!(p->perp_atol >= 0.f) || !(p->norm_eps >= 0.f) || !(p->cell_size >= 0.f))
+        return fail(h, TM_ERR_INVALID, "tm_params: perp_atol, norm_eps and cell_size must be >= 0%s%s");
+    if (p->reserved[0] != 0 || p->reserved[1] != 0) return fail(h, TM_ERR_INVALID, "tm_params.reserved must be 0%s%s");
+    return TM_OK;
+}
+
+static int label_dispatch(tm_handle *h, const LabelArgs &a) {
+    int mode = a.prm.mode;
+    if (mode == TM_MODE_AUTO) {
+        // the grid costs ~10 launches plus binning; exhaustive search wins while N*M is small
+        const double pairs = static_cast<double>(a.n) * static_cast<double>(h->m);
+        mode = (pairs <= 3.0e7 || h->m <= 48) ? TM_MODE_BRUTE : TM_MODE_GRID;
+    }
+    if (mode == TM_MODE_BRUTE) {
+        h->stats.mode_used = TM_MODE_BRUTE;
+        return label_brute(h, a);
+    }
+    return label_grid(h, a);
+}
+
+int tm_label_points(tm_handle *h, const float *pts, int64_t n, int64_t row_stride, const tm_params *params, int32_t *out_index,
+                    int32_t *out_id, float *out_dist, float *out_offset, float *out_radius, void *stream) {
+    if (!h) return TM_ERR_INVALID;
+    int rc = check_params(h, params);
+    if (rc != TM_OK) return rc;
+    if (n < 0) return fail(h, TM_ERR_INVALID, "tm_label_points: negative point count%s%s");
+    if (n == 0) return TM_OK;
+    if (!pts || row_stride < 3) return fail(h, TM_ERR_INVALID, "tm_label_points: null points or row_stride < 3%s%s");
+    if (!h->have_cyl) return fail(h, TM_ERR_STATE, "tm_label_points called before tm_set_cylinders%s%s");
+    if (h->m == 0) return fail(h, TM_ERR_NO_CYLINDERS, "%s%s", tm_status_string(TM_ERR_NO_CYLINDERS));
+    TM_CUDA(h, cudaSetDevice(h->device));
+    h->stats = tm_stats{};
+    LabelArgs a{pts, n, row_stride, *params, out_index, out_id, out_dist, out_offset, out_radius,
+                static_cast<cudaStream_t>(stream)};
+    for (bool &b : h->phase_hit) b = false;
+    mark(h, 0, a.stream);
+    rc = label_dispatch(h, a);
+    mark(h, 9, a.stream);
+    return rc;
+}
+
+int tm_assemble_records(tm_handle *h, const void *cloud, int32_t dtype, int64_t n, int64_t row_stride, const float *offset,
+                        const int32_t *id, double *out, void *stream) {
+    if (!h) return TM_ERR_INVALID;
+    if (n < 0) return fail(h, TM_ERR_INVALID, "tm_assemble_records: negative point count%s%s");
+    if (n == 0) return TM_OK;
+    if (!cloud || !offset || !id || !out || row_stride < 3 || (dtype != TM_F32 && dtype != TM_F64))
+        return fail(h, TM_ERR_INVALID, "tm_assemble_records: bad argument%s%s");
+    TM_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = static_cast<int>(std::min<int64_t>((n * 7 + 255) / 256, static_cast<int64_t>(h->sm_count) * 32));
+    if (dtype == TM_F32) assemble_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(cloud), n, row_stride, offset, id, out);
+    else assemble_kernel<double><<<blocks, 256, 0, st>>>(static_cast<const double *>(cloud), n, row_stride, offset, id, out);
+    TM_CUDA(h, cudaGetLastError());
+    return TM_OK;
+}
+
+// ---- pipelined host entry -----------------------------------------------------------------------
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride,
+                        const tm_params *params, double *out_records_host, float *out_dist_host) {
+    if (!h) return TM_ERR_INVALID;
+    int rc = check_params(h, params);
+    if (rc != TM_OK) return rc;
+    if (n < 0) return fail(h, TM_ERR_INVALID, "tm_label_cloud_host: negative point count%s%s");
+    if (n == 0) return TM_OK;
+    if (!cloud_host || !out_records_host || row_stride < 3 || (dtype != TM_F32 && dtype != TM_F64))
+        return fail(h, TM_ERR_INVALID, "tm_label_cloud_host: bad argument%s%s");
+    if (!h->have_cyl) return fail(h, TM_ERR_STATE, "tm_label_cloud_host called before tm_set_cylinders%s%s");
+    if (h->m == 0) return fail(h, TM_ERR_NO_CYLINDERS, "%s%s", tm_status_string(TM_ERR_NO_CYLINDERS));
+    TM_CUDA(h, cudaSetDevice(h->device));
+    for (auto &s : h->pipe_stream) if (!s) TM_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &e : h->pipe_event) if (!e) TM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t s_in = h->pipe_stream[0], s_cmp = h->pipe_stream[1], s_out = h->pipe_stream[2];
+
+    int64_t chunk = 1 << 20;
+    if (const char *env = getenv("TM_HOST_CHUNK")) { const long long v = atoll(env); if (v >= 1024) chunk = v; }
+    chunk = std::min(chunk, n);
+    const size_t esz = dtype == TM_F32 ? 4 : 8;
+    const bool in_pinned = host_is_pinned(cloud_host);
+    const bool out_pinned = host_is_pinned(out_records_host) && (!out_dist_host || host_is_pinned(out_dist_host));
+    const size_t in_bytes = static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+    const size_t rec_bytes = static_cast<size_t>(chunk) * 7 * sizeof(double);
+    const size_t out_bytes = rec_bytes + static_cast<size_t>(chunk) * sizeof(float);
+    for (int b = 0; b < 2; ++b) {
+        if (!in_pinned && h->pinned_in_cap < in_bytes) {
+            if (h->pinned_in[b]) { cudaFreeHost(h->pinned_in[b]); h->pinned_in[b] = nullptr; }
+            TM_CUDA(h, cudaMallocHost(&h->pinned_in[b], in_bytes));
+        }
+        if (!out_pinned && h->pinned_out_cap < out_bytes) {
+            if (h->pinned_out[b]) { cudaFreeHost(h->pinned_out[b]); h->pinned_out[b] = nullptr; }
+            TM_CUDA(h, cudaMallocHost(&h->pinned_out[b], out_bytes));
+        }
+        TM_CUDA(h, h->chunk_in[b].ensure(in_bytes + (dtype == TM_F64 ? static_cast<size_t>(chunk) * 12 : 0)));
+        TM_CUDA(h, h->chunk_rec[b].ensure(rec_bytes));
+        TM_CUDA(h, h->chunk_off[b].ensure(static_cast<size_t>(chunk) * 12));
+        TM_CUDA(h, h->chunk_id[b].ensure(static_cast<size_t>(chunk) * 4));
+        TM_CUDA(h, h->chunk_dist[b].ensure(static_cast<size_t>(chunk) * 4));
+    }
+    if (!in_pinned) h->pinned_in_cap = std::max(h->pinned_in_cap, in_bytes);
+    if (!out_pinned) h->pinned_out_cap = std::max(h->pinned_out_cap, out_bytes);
+
+    // events: [0,1] H2D done per buffer, [2,3] compute done, [4,5] D2H done, [6,7] compute consumed input
+    tm_stats total{};
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const unsigned char *src = static_cast<const unsigned char *>(cloud_host);
+    auto drain_out = [&](int64_t c) -> int {           // copy a finished chunk from pinned staging to the caller
+        const int b = static_cast<int>(c & 1);
+        TM_CUDA(h, cudaEventSynchronize(h->pipe_event[4 + b]));
+        if (!out_pinned) {
+            const int64_t cnt = std::min(chunk, n - c * chunk);
+            memcpy(out_records_host + c * chunk * 7, h->pinned_out[b], static_cast<size_t>(cnt) * 7 * sizeof(double));
+            if (out_dist_host)
+                memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b]) + rec_bytes,
+                       static_cast<size_t>(cnt) * sizeof(float));
+        }
+        return TM_OK;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t cnt = std::min(chunk, n - c * chunk);
+        const size_t bytes = static_cast<size_t>(cnt) * static_cast<size_t>(row_stride) * esz;
+        const unsigned char *csrc = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+        if (c >= 2) {
+            // buffer b is being reused: its previous output must have left the device and the staging area
+            rc = drain_out(c - 2);
+            if (rc != TM_OK) return rc;
+            TM_CUDA(h, cudaStreamWaitEvent(s_in, h->pipe_event[6 + b], 0));
+        }
+        if (!in_pinned) {
+            memcpy(h->pinned_in[b], csrc, bytes);
+            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b], bytes, cudaMemcpyHostToDevice, s_in));
+        } else {
+            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
+        }
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[0 + b], s_in));
+        TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[0 + b], 0));
+        if (c >= 2) TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[4 + b], 0));   // records buffer b free again
+        const float *pts32;
+        int64_t stride32;
+        if (dtype == TM_F64) {
+            float *conv = reinterpret_cast<float *>(h->chunk_in[b].as<unsigned char>() + in_bytes);
+            const int blocks = static_cast<int>(std::min<int64_t>((cnt * 3 + 255) / 256, static_cast<int64_t>(h->sm_count) * 32));
+            f64_to_f32_xyz_kernel<<<blocks, 256, 0, s_cmp>>>(h->chunk_in[b].as<double>(), cnt, row_stride, conv);
+            TM_CUDA(h, cudaGetLastError());
+            pts32 = conv;
+            stride32 = 3;
+        } else {
+            pts32 = h->chunk_in[b].as<float>();
+            stride32 = row_stride;
+        }
+        h->stats = tm_stats{};
+        LabelArgs a{pts32, cnt, stride32, *params, nullptr, h->chunk_id[b].as<int32_t>(),
+                    out_dist_host ? h->chunk_dist[b].as<float>() : nullptr, h->chunk_off[b].as<float>(), nullptr, s_cmp};
+        rc = label_dispatch(h, a);
+        if (rc != TM_OK) return rc;
+        total.pairs_evaluated += h->stats.pairs_evaluated;
+        total.points_brute += h->stats.points_brute;
+        total.mode_used = h->stats.mode_used;
+        rc = tm_assemble_records(h, h->chunk_in[b].p, dtype, cnt, row_stride, h->chunk_off[b].as<float>(),
+                                 h->chunk_id[b].as<int32_t>(), h->chunk_rec[b].as<double>(), s_cmp);
+        if (rc != TM_OK) return rc;
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[2 + b], s_cmp));
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[6 + b], s_cmp));
+        TM_CUDA(h, cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
+        double *dst_rec = out_pinned ? out_records_host + c * chunk * 7 : static_cast<double *>(h->pinned_out[b]);
+        TM_CUDA(h, cudaMemcpyAsync(dst_rec, h->chunk_rec[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double),
+                                   cudaMemcpyDeviceToHost, s_out));
+        if (out_dist_host) {
+            float *dst_d = out_pinned ? out_dist_host + c * chunk
+                                      : reinterpret_cast<float *>(static_cast<unsigned char *>(h->pinned_out[b]) + rec_bytes);
+            TM_CUDA(h, cudaMemcpyAsync(dst_d, h->chunk_dist[b].p, static_cast<size_t>(cnt) * sizeof(float),
+                                       cudaMemcpyDeviceToHost, s_out));
+        }
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[4 + b], s_out));
+    }
+    for (int64_t c = std::max<int64_t>(0, nchunks - 2); c < nchunks; ++c) {
+        rc = drain_out(c);
+        if (rc != TM_OK) return rc;
+    }
+    TM_CUDA(h, cudaStreamSynchronize(s_out));
+    TM_CUDA(h, cudaStreamSynchronize(s_cmp));
+    h->stats.pairs_evaluated = total.pairs_evaluated;
+    h->stats.points_brute = total.points_brute;
+    return TM_OK;
+}
+
+int tm_get_stats(tm_handle *h, tm_stats *out) {
+    if (!h || !out) return TM_ERR_INVALID;
+    TM_CUDA(h, cudaSetDevice(h->device));
+    TM_CUDA(h, cudaDeviceSynchronize());
+    tm_stats s = h->stats;
+    if (s.mode_used == TM_MODE_GRID && h->dstats.p) {
+        tmn::DevStats d;
+        TM_CUDA(h, cudaMemcpy(&d, h->dstats.p, sizeof(d), cudaMemcpyDeviceToHost));
+        s.pairs_evaluated += d.pairs_grid + static_cast<uint64_t>(d.outliers) * static_cast<uint64_t>(h->m);
+        s.points_grid = s.points_grid >= d.outliers ? s.points_grid - d.outliers : 0;   // label_grid stored N here
+        s.points_brute += d.outliers;
+        s.tile_entries = d.tile_entries;
+        s.voxels_occupied = d.voxels_occupied;
+        s.voxels_brute = d.voxels_brute;
+        s.work_items = d.work_items;
+        s.cell_size = h->grid.h;
+        s.grid_dim[0] = static_cast<uint32_t>(h->grid.nx);
+        s.grid_dim[1] = static_cast<uint32_t>(h->grid.ny);
+        s.grid_dim[2] = static_cast<uint32_t>(h->grid.nz);
+    }
+    *out = s;
+    return TM_OK;
+}
+
+int tm_set_profiling(tm_handle *h, int enabled) {
+    if (!h) return TM_ERR_INVALID;
+    h->profiling = enabled != 0;
+    return TM_OK;
+}
+
+int tm_get_phase_ms(tm_handle *h, float *out_ms) {
+    if (!h || !out_ms) return TM_ERR_INVALID;
+    for (int i = 0; i < TM_PHASES; ++i) out_ms[i] = 0.f;
+    if (!h->profiling || !h->phase_hit[0] || !h->phase_hit[9]) return TM_OK;
+    TM_CUDA(h, cudaSetDevice(h->device));
+    TM_CUDA(h, cudaEventSynchronize(h->phase_ev[9]));
+    // phase p spans mark p -> the next mark that was recorded
+    for (int p = 0; p < 7; ++p) {
+        if (!h->phase_hit[p] ) continue;
+        int q = p + 1;
+        while (q < 9 && !h->phase_hit[q]) ++q;
+        if (p == 0 && !h->phase_hit[1]) continue;          // brute mode has no binning phase
+        TM_CUDA(h, cudaEventElapsedTime(&out_ms[p], h->phase_ev[p], h->phase_ev[q]));
+    }
+    TM_CUDA(h, cudaEventElapsedTime(&out_ms[7], h->phase_ev[0], h->phase_ev[9]));
+    return TM_OK;
+}
+
+int tm_measure_fp32_peak(tm_handle *h, double *lane_ops_per_second) {
+    if (!h || !lane_ops_per_second) return TM_ERR_INVALID;
+    TM_CUDA(h, cudaSetDevice(h->device));
+    TM_CUDA(h, h->scratch_f.ensure(256));
+    cudaEvent_t e0, e1;
+    TM_CUDA(h, cudaEventCreate(&e0));
+    TM_CUDA(h, cudaEventCreate(&e1));
+    const int blocks = h->sm_count * 8, iters = 8192;
+    double best = 0.0;
+    for (int kind = 0; kind < 2; ++kind) {
+        for (int rep = 0; rep < 4; ++rep) {
+            TM_CUDA(h, cudaEventRecord(e0, 0));
+            if (kind == 0) fp32_probe_kernel<0><<<blocks, 256>>>(h->scratch_f.as<float>(), iters, 1.0000001f, 1e-7f);
+            else fp32_probe_kernel<1><<<blocks, 256>>>(h->scratch_f.as<float>(), iters, 1.0000001f, 1e-7f);
+            TM_CUDA(h, cudaEventRecord(e1, 0));
+            TM_CUDA(h, cudaEventSynchronize(e1));
+            float ms = 0.f;
+            TM_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+            const double ops = static_cast<double>(blocks) * 256.0 * iters * 8.0;
+            if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    TM_CUDA(h, cudaGetLastError());
+    *lane_ops_per_second = best;
+    return TM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// Exhaustive nearest-cylinder kernel: every (point, cylinder) pair, cylinders streamed through
+// shared memory in TMA-staged tiles.  It is
+//   * the FP32-roofline yard-stick (pairs = N*M exactly, no accounting ambiguity),
+//   * the small-M path of the QSM-fitting call site (QSMFittingDepthFirst.py:1079-1081),
+//   * the fallback for points the voxel grid cannot answer (outside the grid, non-finite, voxels
+//     whose candidate tile would be too large).
+// Replaces the (N_b, M, 3) broadcast chain of LabelGenerationCuda.py:36-88 / Projection.py:35-91.
+#include <algorithm>
+
+#include "tm_core.cuh"
+#include "tm_eval.cuh"
+#include "tm_ptx.cuh"
+
+namespace tmn {
+
+constexpr int BRUTE_THREADS = 256;
+constexpr int BRUTE_TILE = 512;          // cylinders per stage: 2 x 8 KB (A and B records)
+constexpr int BRUTE_STAGES = 2;
+
+// One thread owns P points (registers); the CTA walks the cylinder table tile by tile.  A single
+// elected thread arms the stage's mbarrier and issues two bulk copies (A records, B records) for
+// tile t+1 while all threads evaluate tile t from shared memory: every LDS is a 128-bit broadcast.
+// gridDim.y splits the table so small point sets still fill the machine; partial winners meet in
+// a 64-bit atomicMin on the (distance, index) key, which is torch.argmin's comparator.
+template <int P, bool GUARD, bool NFMA>
+__global__ void __launch_bounds__(BRUTE_THREADS)
+brute_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, const int32_t *__restrict__ sel,
+             const unsigned int *__restrict__ d_count, const float4 *__restrict__ recA,
+             const float4 *__restrict__ recB, int m, int tiles_per_split, float atol, float eps,
+             unsigned long long *__restrict__ keys, int use_atomic) {
+    __shared__ __align__(128) float4 sA[BRUTE_STAGES][BRUTE_TILE];
+    __shared__ __align__(128) float4 sB[BRUTE_STAGES][BRUTE_TILE];
+    __shared__ __align__(8) uint64_t full[BRUTE_STAGES];
+
+    const int tid = threadIdx.x;
+    const int64_t n_eff = d_count ? static_cast<int64_t>(*d_count) : n;
+    const int ntiles = (m + BRUTE_TILE - 1) / BRUTE_TILE;
+    const int t_begin = blockIdx.y * tiles_per_split;
+    const int t_end = min(ntiles, t_begin + tiles_per_split);
+    if (t_begin >= t_end) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < BRUTE_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t issued = 0, consumed = 0;       // running tile counters → stage = c % STAGES, parity = (c / STAGES) & 1
+    auto issue = [&](int t) {
+        const int s = issued % BRUTE_STAGES;
+        const int base = t * BRUTE_TILE;
+        const uint32_t cnt = static_cast<uint32_t>(min(BRUTE_TILE, m - base));
+        mbar_expect_tx(&full[s], cnt * 32u);
+        bulk_g2s(&sA[s][0], recA + base, cnt * 16u, &full[s]);
+        bulk_g2s(&sB[s][0], recB + base, cnt * 16u, &full[s]);
+    };
+
+    constexpr int PTS = BRUTE_THREADS * P;
+    for (int64_t blk = blockIdx.x; blk * PTS < n_eff; blk += gridDim.x) {
+        float px[P], py[P], pz[P], bestd[P];
+        uint32_t besti[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            int64_t slot = blk * PTS + k * BRUTE_THREADS + tid;
+            if (slot >= n_eff) slot = n_eff - 1;                    // duplicate work, masked at the store
+            const int64_t row = sel ? static_cast<int64_t>(sel[slot]) : slot;
+            const float *p = pts + row * row_stride;
+            px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+            bestd[k] = __int_as_float(0x7f800000);                  // +inf
+            besti[k] = static_cast<uint32_t>(t_begin) * BRUTE_TILE; // all-inf row → lowest index
+        }
+
+        if (tid == 0) { issue(t_begin); }
+        ++issued;
+        for (int t = t_begin; t < t_end; ++t) {
+            if (t + 1 < t_end) {
+                if (tid == 0) issue(t + 1);     // its buffer was released by the barrier ending tile t-1
+                ++issued;
+            }
+            const int s = consumed % BRUTE_STAGES;
+            mbar_wait(&full[s], (consumed / BRUTE_STAGES) & 1);
+            ++consumed;
+            const int base = t * BRUTE_TILE;
+            const int cnt = min(BRUTE_TILE, m - base);
+#pragma unroll 2
+            for (int j = 0; j < cnt; ++j) {
+                const float4 a = sA[s][j];
+                const float4 b = sB[s][j];
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    const float d = eval_pair<GUARD, NFMA, false>(px[k], py[k], pz[k], a, b, atol, eps, nullptr);
+                    // ascending index order: the newcomer wins iff the incumbent is not NaN and
+                    // (newcomer is NaN or strictly smaller)  — LessOrNan with lowest-index ties
+                    const bool wins = !(d >= bestd[k]) && (bestd[k] == bestd[k]);
+                    bestd[k] = wins ? d : bestd[k];
+                    besti[k] = wins ? static_cast<uint32_t>(base + j) : besti[k];
+                }
+            }
+            __syncthreads();                    // everyone is done with stage s → it may be refilled
+            fence_proxy_async();
+        }
+
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            const int64_t slot = blk * PTS + k * BRUTE_THREADS + tid;
+            if (slot < n_eff) {
+                const unsigned long long key = make_key(bestd[k], besti[k]);
+                if (use_atomic) atomicMin(keys + slot, key);
+                else keys[slot] = key;
+            }
+        }
+    }
+}
+
+// Winner-only epilogue for the exhaustive path (fused label + offset write, A:92-109): recompute the
+// winning pair with full geometry (bit-identical distance), move to the mantle, gather the ID.
+template <bool GUARD, bool NFMA>
+__global__ void __launch_bounds__(256)
+finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, const int32_t *__restrict__ sel,
+                const unsigned int *__restrict__ d_count, const unsigned long long *__restrict__ keys,
+                const float4 *__restrict__ recA, const float4 *__restrict__ recB, const int32_t *__restrict__ ids,
+                float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index,
+                int32_t *__restrict__ out_id, float *__restrict__ out_dist, float *__restrict__ out_offset,
+                float *__restrict__ out_radius) {
+    const int64_t n_eff = d_count ? static_cast<int64_t>(*d_count) : n;
+    for (int64_t slot = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; slot < n_eff;
+         slot += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = sel ? static_cast<int64_t>(sel[slot]) : slot;
+        const uint32_t j = key_index(keys[slot]);
+        const float *p = pts + row * row_stride;
+        const float px = p[0], py = p[1], pz = p[2];
+        const float4 a = recA[j], b = recB[j];
+        PairGeom g;
+        eval_pair<GUARD, NFMA, true>(px, py, pz, a, b, atol, eps, &g);
+        float ox, oy, oz;
+        mantle_offset<NFMA>(g, px, py, pz, move_to_mantle != 0, ox, oy, oz);
+        if (out_index) out_index[row] = static_cast<int32_t>(j);
+        if (out_id) out_id[row] = ids[j];
+        if (out_dist) out_dist[row] = g.dist;
+        if (out_offset) { out_offset[3 * row] = ox; out_offset[3 * row + 1] = oy; out_offset[3 * row + 2] = oz; }
+        if (out_radius) out_radius[row] = b.w;
+    }
+}
+
+template <int P, bool GUARD, bool NFMA>
+static cudaError_t launch_brute(dim3 grid, cudaStream_t st, const float *pts, int64_t n, int64_t rs, const int32_t *sel,
+                                const unsigned int *d_count, const float4 *A, const float4 *B, int m, int tps, float atol,
+                                float eps, unsigned long long *keys, int use_atomic) {
+    brute_kernel<P, GUARD, NFMA><<<grid, BRUTE_THREADS, 0, st>>>(pts, n, rs, sel, d_count, A, B, m, tps, atol, eps, keys,
+                                                                use_atomic);
+    return cudaGetLastError();
+}
+
+static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const unsigned int *d_count, int64_t n_launch) {
+    const bool guard = a.prm.norm_eps > 0.f;
+    const bool nfma = a.prm.norm_fma != 0;
+    const int m = static_cast<int>(h->m);
+    const int ntiles = (m + BRUTE_TILE - 1) / BRUTE_TILE;
+    TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * static_cast<size_t>(n_launch)));
+    unsigned long long *keys = h->keys.as<unsigned long long>();
+
+    int P, splits;
+    int64_t nblk;
+    if (d_count) {
+        // the true count is only known on the device (outliers of the grid path, normally a handful):
+        // a fixed launch that strides over however many points there are, table split 32 ways
+        P = 1;
+        nblk = std::min<int64_t>((n_launch + BRUTE_THREADS - 1) / BRUTE_THREADS, h->sm_count);
+        splits = std::min(ntiles, 32);
+    } else {
+        // points per thread: 2 once there are enough points to fill the machine twice over
+        const int64_t full_wave = static_cast<int64_t>(h->sm_count) * 3 * BRUTE_THREADS;
+        P = (n_launch >= 4 * full_wave) ? 2 : 1;
+        nblk = (n_launch + BRUTE_THREADS * P - 1) / (BRUTE_THREADS * P);
+        const int64_t want_ctas = static_cast<int64_t>(h->sm_count) * 6;
+        splits = 1;
+        if (nblk < want_ctas) splits = static_cast<int>(std::min<int64_t>(ntiles, (want_ctas + nblk - 1) / nblk));
+    }
+    if (splits > 65535) splits = 65535;
+    const int tps = (ntiles + splits - 1) / splits;
+    splits = (ntiles + tps - 1) / tps;
+    const int use_atomic = splits > 1;
+    if (use_atomic) TM_CUDA(h, cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * static_cast<size_t>(n_launch), a.stream));
+    dim3 grid(static_cast<unsigned>(std::min<int64_t>(nblk, 1 << 20)), static_cast<unsigned>(splits));
+    const float4 *A = h->recA.as<float4>();
+    const float4 *B = h->recB.as<float4>();
+    if (!d_count) mark(h, 5, a.stream);
+    cudaError_t e;
+#define TM_BRUTE_CASE(PP, G, F)                                                                                   \
+    e = launch_brute<PP, G, F>(grid, a.stream, a.pts, n_launch, a.row_stride, sel, d_count, A, B, m, tps,           \
+                               a.prm.perp_atol, a.prm.norm_eps, keys, use_atomic)
+    if (P == 2) {
+        if (guard) { if (nfma) TM_BRUTE_CASE(2, true, true); else TM_BRUTE_CASE(2, true, false); }
+        else       { if (nfma) TM_BRUTE_CASE(2, false, true); else TM_BRUTE_CASE(2, false, false); }
+    } else {
+        if (guard) { if (nfma) TM_BRUTE_CASE(1, true, true); else TM_BRUTE_CASE(1, true, false); }
+        else       { if (nfma) TM_BRUTE_CASE(1, false, true); else TM_BRUTE_CASE(1, false, false); }
+    }
+#undef TM_BRUTE_CASE
+    TM_CUDA(h, e);
+
+    mark(h, 6, a.stream);
+    const int fgrid = static_cast<int>(std::min<int64_t>((n_launch + 255) / 256, static_cast<int64_t>(h->sm_count) * 16));
+#define TM_FIN_CASE(G, F)                                                                                          \
+    finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, n_launch, a.row_stride, sel, d_count, keys, A, B,     \
+                                                       h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
+                                                       a.prm.move_to_mantle, a.out_index, a.out_id, a.out_dist,     \
+                                                       a.out_offset, a.out_radius)
+    if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
+    else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
+#undef TM_FIN_CASE
+    TM_CUDA(h, cudaGetLastError());
+    return TM_OK;
+}
+
+int label_brute(tm_handle *h, const LabelArgs &a) {
+    if (a.n == 0) return TM_OK;
+    int rc = run_brute(h, a, nullptr, nullptr, a.n);
+    if (rc != TM_OK) return rc;
+    h->stats.pairs_evaluated += static_cast<uint64_t>(a.n) * static_cast<uint64_t>(h->m);
+    h->stats.points_brute += static_cast<uint64_t>(a.n);
+    return TM_OK;
+}
+
+int label_brute_subset(tm_handle *h, const LabelArgs &a, const int32_t *sel, const unsigned int *d_count,
+                       unsigned int max_count) {
+    if (max_count == 0) return TM_OK;
+    // the true count lives on the device; launch for a modest grid and let the kernel stride
+    const int64_t n_launch = std::min<int64_t>(max_count, a.n);
+    return run_brute(h, a, sel, d_count, n_launch);
+}
+
+}  // namespace tmn

@@ -1,0 +1,163 @@
+// Shared declarations of the library's translation units: the handle, scratch buffers, error
+// plumbing and the internal entry points of the brute-force and voxel-grid paths.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/treemorph_nn.h"
+
+namespace tmn {
+
+// grow-only device scratch buffer owned by the handle
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+// Uniform voxel grid over the cylinders' solid AABBs (plus a margin).  Voxel (x,y,z) has the
+// linear id morton-interleaved over (bits.x, bits.y, bits.z) so that neighbouring voxels are
+// neighbours in memory and consecutive work items share candidate cylinders in L1/L2.
+struct GridDesc {
+    float ox, oy, oz;        // world position of the corner of voxel (0,0,0)
+    float h, inv_h;          // voxel edge
+    int nx, ny, nz;          // extent in voxels
+    int bx, by, bz;          // bits per axis of the interleaved id
+    uint32_t ncell_codes;    // 1 << (bx+by+bz): size of the per-voxel arrays
+};
+
+// device-side counters of one labelling call (mirrors tm_stats where it is data dependent)
+struct DevStats {
+    unsigned long long pairs_grid;
+    unsigned long long tile_entries;
+    unsigned long long points_grid;
+    unsigned int voxels_occupied;
+    unsigned int voxels_brute;
+    unsigned int work_items;
+    unsigned int outliers;          // points routed to the exhaustive kernel
+    unsigned int tile_pool_used;    // entries (multiple of 4 per tile)
+    unsigned int pad;
+};
+
+}  // namespace tmn
+
+struct tm_handle {
+    int device = 0;
+    int sm_count = 148;
+    char err[512] = {0};
+
+    // ---- cylinder table (tm_set_cylinders) ----
+    int64_t m = 0;
+    bool have_cyl = false;
+    tmn::DevBuf recA, recB;          // float4[M]: {start.xyz, axis_length}, {unit.xyz, radius}
+    tmn::DevBuf ids;                 // int32[M]
+    tmn::DevBuf boxlo, boxhi;        // float4[M]: solid-cylinder AABB (w unused)
+    tmn::DevBuf bbox;                // 6 floats as ordered ints: global min/max + counters
+
+    // ---- static voxel index of the cylinders ----
+    bool have_grid = false;
+    float grid_cell = 0.f;          // cell size the index was built with
+    tmn::GridDesc grid{};
+    tmn::DevBuf cyl_cell_start;      // uint32[ncell_codes + 1]: CSR offsets of the home lists
+    tmn::DevBuf cyl_cell_list;       // int32[]: cylinder rows per voxel
+    tmn::DevBuf long_list;           // int32[]: cylinders whose AABB spans too many voxels
+    tmn::DevBuf special;             // int32[]: non-finite cylinders, evaluated for every point
+    uint32_t n_long = 0, n_special = 0, n_listed = 0;
+    uint64_t cyl_list_len = 0;
+
+    // ---- per-call scratch ----
+    tmn::DevBuf keys;                // u64 per point (brute) / per outlier
+    tmn::DevBuf pt_cell, pt_rank;    // uint32 per point
+    tmn::DevBuf cell_count, cell_start, block_sums;
+    tmn::DevBuf sorted_pts;          // float4 per point {x,y,z,bits(original row)}
+    tmn::DevBuf occ_cells;           // uint32 per occupied voxel
+    tmn::DevBuf tile_meta;           // uint4 per occupied voxel
+    tmn::DevBuf tileA, tileB, tileI; // candidate tile pool
+    tmn::DevBuf items;               // uint4 per work item
+    tmn::DevBuf outlier_idx;         // int32 original rows routed to the exhaustive kernel
+    tmn::DevBuf dstats;              // tmn::DevStats + cursors
+    tmn::DevBuf scratch_f;           // misc float scratch (strided-input staging)
+    size_t tile_pool_entries = 0;
+
+    // ---- host pipeline (tm_label_cloud_host) ----
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_event[8] = {nullptr};
+    void *pinned_in[2] = {nullptr, nullptr};
+    void *pinned_out[2] = {nullptr, nullptr};
+    size_t pinned_in_cap = 0, pinned_out_cap = 0;
+    tmn::DevBuf chunk_in[2], chunk_rec[2], chunk_off[2], chunk_id[2], chunk_dist[2];
+
+    // ---- optional phase timing ----
+    bool profiling = false;
+    cudaEvent_t phase_ev[10] = {nullptr};
+    bool phase_hit[10] = {false};
+
+    tm_stats stats{};
+};
+
+namespace tmn {
+
+inline int fail(tm_handle *h, int code, const char *fmt, const char *a = "", const char *b = "") {
+    if (h) snprintf(h->err, sizeof(h->err), fmt, a, b);
+    return code;
+}
+
+#define TM_CUDA(h, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            return tmn::fail((h), _e == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA,   \
+                            "%s failed: %s", #expr, cudaGetErrorString(_e));                     \
+        }                                                                                        \
+    } while (0)
+
+// phase marks: event i is recorded when phase i-1 ends / phase i begins (0 = call start, 9 = call end)
+inline void mark(tm_handle *h, int i, cudaStream_t st) {
+    if (!h->profiling) return;
+    if (!h->phase_ev[i]) cudaEventCreate(&h->phase_ev[i]);
+    cudaEventRecord(h->phase_ev[i], st);
+    h->phase_hit[i] = true;
+}
+
+struct LabelArgs {
+    const float *pts;
+    int64_t n;
+    int64_t row_stride;
+    tm_params prm;
+    int32_t *out_index;
+    int32_t *out_id;
+    float *out_dist;
+    float *out_offset;
+    float *out_radius;
+    cudaStream_t stream;
+};
+
+// tm_brute.cu
+int label_brute(tm_handle *h, const LabelArgs &a);
+// exhaustive search for a subset of points given by original row indices (device array, count on device)
+int label_brute_subset(tm_handle *h, const LabelArgs &a, const int32_t *sel, const unsigned int *d_count,
+                       unsigned int max_count);
+// tm_grid.cu
+int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream);
+int label_grid(tm_handle *h, const LabelArgs &a);
+float auto_cell_size(const tm_handle *h, int64_t n);
+
+}  // namespace tmn

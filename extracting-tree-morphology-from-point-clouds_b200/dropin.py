@@ -1,0 +1,89 @@
+"""Shared body of the two drop-in modules.
+
+``PreProcessing/LabelGenerationCuda.py`` and ``Modules/Projection.py`` of the reference carry two copies
+of the same kernel that differ in three constants; here one implementation is
+parameterised by ``api.Variant`` and both modules forward to it.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import api
+
+QSM_COLUMNS = ("startX", "startY", "startZ", "endX", "endY", "endZ", "radius", "ID")
+
+_table_key: dict[int, tuple] = {}          # device index -> identity of the installed cylinder tensors
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"closest_cylinder_cuda_batch needs a CUDA device, got {dev}: "
+                           "the B200 path has no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _identity(*tensors) -> tuple:
+    return tuple((t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version) for t in tensors)
+
+
+def closest_cylinder(points, start, radius, axis_length, axis_unit, IDs, device, variant: api.Variant,
+                     move_points_to_mantle: bool = True):
+    """``closest_cylinder_cuda_batch`` (LabelGenerationCuda.py:20-111 / Projection.py:19-115).
+
+    points: (N,3) array-like or tensor; cylinder arguments: torch tensors (any strides) or array-likes.
+    Returns host numpy ``(ids int32 (N,), distances float32 (N,), offsets float32 (N,3))``.
+    """
+    dev = _cuda_device(device)
+    eng = api.get_engine(dev)
+    cyl = []
+    for t, dt in ((start, torch.float32), (radius, torch.float32), (axis_length, torch.float32),
+                  (axis_unit, torch.float32), (IDs, torch.int32)):
+        t = torch.as_tensor(t)
+        if t.device != dev or t.dtype != dt:
+            t = t.to(device=dev, dtype=dt)
+        cyl.append(t)
+    start_t, radius_t, length_t, unit_t, ids_t = cyl
+    key = _identity(*cyl)
+    if _table_key.get(dev.index) != key:
+        eng.set_cylinders(start_t, radius_t, length_t, unit_t, ids_t)
+        _table_key[dev.index] = key
+    m = start_t.shape[0]
+    # ATen rounds norm() differently for a contiguous xyz axis (C-ordered tensors, or M == 1) than for
+    # the Fortran-ordered tensors the DataFrame path produces; mirror whichever the caller's layout implies.
+    norm_fma = m <= 1 or start_t.stride(1) == 1
+    pts = torch.as_tensor(np.asarray(points) if not isinstance(points, torch.Tensor) else points)
+    pts = pts.to(device=dev, dtype=torch.float32)            # torch.tensor(points, dtype=float32, device=device)
+    res = eng.label(pts, variant, move_to_mantle=move_points_to_mantle, norm_fma=norm_fma,
+                    want=("id", "dist", "offset"))
+    return res["id"].cpu().numpy(), res["dist"].cpu().numpy(), res["offset"].cpu().numpy()
+
+
+def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None, batch_size=1024):
+    """``generate_offset_cloud_cuda_batched`` (LabelGenerationCuda.py:113-135 / Projection.py:117-144).
+
+    cloud: (N, >=3) array; cylinders: DataFrame with the QSM columns.  Returns float64 (N,7)
+    ``[x, y, z, ox, oy, oz, ID]``.  ``batch_size`` is accepted for signature compatibility; results do not
+    depend on it (each point is independent), so the whole cloud is processed in pipelined chunks.
+    """
+    del masterBar, batch_size
+    dev = _cuda_device(device)
+    eng = api.get_engine(dev)
+    start = torch.as_tensor(np.ascontiguousarray(cylinders[["startX", "startY", "startZ"]].values, dtype=np.float32), device=dev)
+    end = torch.as_tensor(np.ascontiguousarray(cylinders[["endX", "endY", "endZ"]].values, dtype=np.float32), device=dev)
+    radius = torch.as_tensor(np.ascontiguousarray(cylinders["radius"].values, dtype=np.float32), device=dev)
+    ids = torch.as_tensor(np.ascontiguousarray(cylinders["ID"].values).astype(np.int32), device=dev)
+    m = start.shape[0]
+    norm_fma = m <= 1                        # DataFrame tensors are Fortran-ordered in the reference (strided norm)
+    length, unit = eng.prepare(start, end, variant, norm_fma=norm_fma)
+    eng.set_cylinders(start, radius, length, unit, ids)
+    _table_key.pop(dev.index, None)
+    cloud = np.asarray(cloud)
+    if cloud.ndim != 2 or cloud.shape[1] < 3:
+        raise ValueError(f"cloud must have shape (N, >=3), got {cloud.shape}")
+    if len(cloud) == 0:
+        return np.zeros((0, 7))
+    return eng.label_cloud_host(cloud, variant, norm_fma=norm_fma)

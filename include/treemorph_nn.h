@@ -1,0 +1,184 @@
+/*
+ * treemorph_nn — C ABI of the B200-native nearest-cylinder label + offset path.
+ *
+ * This is the drop-in boundary for ONE hot path of RobinDanek/Extracting-Tree-Morphology-From-Point-Clouds:
+ * the point -> QSM-cylinder search.  The reference has no FFI for it (it is a chain of ~70 ATen
+ * calls per 1024-point batch); its "operator API" is three Python callables per module, and each
+ * entry point below names the reference lines it replaces (paths relative to the reference root):
+ *
+ *   closest_cylinder_cuda_batch         PreProcessing/LabelGenerationCuda.py:20-111   (variant A)
+ *                                       Modules/Projection.py:19-115                  (variant B)
+ *   generate_offset_cloud_cuda_batched  PreProcessing/LabelGenerationCuda.py:113-135
+ *                                       Modules/Projection.py:117-144
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types cross this boundary;
+ *   - every pointer is a DEVICE pointer on the handle's device unless the name ends in `_host`;
+ *   - the caller owns inputs and outputs; the library owns only scratch memory inside the handle;
+ *   - every call returns an int status (TM_OK == 0); tm_last_error() gives the message;
+ *     no exceptions cross the boundary;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise;
+ *   - one handle per (device, host thread); handles are not thread-safe;
+ *   - there is NO CPU fallback: without a CUDA device tm_create() fails.
+ *
+ * The Python side binds this with ctypes and passes tensor.data_ptr() values
+ * (extracting-tree-morphology-from-point-clouds_b200/binding.py); INTEGRATION.md shows the stub.
+ */
+#ifndef TREEMORPH_NN_H
+#define TREEMORPH_NN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TM_ABI_VERSION 1
+
+/* status codes */
+#define TM_OK               0
+#define TM_ERR_INVALID      1   /* bad argument (null pointer, negative size, unknown mode ...)      */
+#define TM_ERR_NO_CYLINDERS 2   /* N > 0 but M == 0: the reference raises in argmin on an empty dim  */
+#define TM_ERR_CUDA         3   /* a CUDA runtime call or kernel failed; see tm_last_error()          */
+#define TM_ERR_NOMEM        4   /* device or pinned-host allocation failed                            */
+#define TM_ERR_STATE        5   /* call order violated (e.g. tm_label_points before tm_set_cylinders) */
+
+/* tm_params.mode */
+#define TM_MODE_AUTO  0         /* grid when N*M is large enough to pay for it, else brute force      */
+#define TM_MODE_BRUTE 1         /* exhaustive tiled kernel: every (point, cylinder) pair              */
+#define TM_MODE_GRID  2         /* voxel-binned points + per-voxel candidate tiles (exact pruning)    */
+
+/* cloud element types for the host/record entry points */
+#define TM_F32 0
+#define TM_F64 1
+
+typedef struct tm_handle tm_handle;
+
+/*
+ * The knobs that distinguish the reference's two copies of the kernel.
+ *   variant A (LabelGenerationCuda.py): perp_atol 1e-6 (:51), norm_eps 0   (:58-60, unguarded)
+ *   variant B (Projection.py):          perp_atol 1e-3 (:50), norm_eps 1e-8 (:60-63)
+ */
+typedef struct tm_params {
+    float   perp_atol;       /* isclose(dot, 0, atol) tolerance                                       */
+    float   norm_eps;        /* lower guard on ||rejection|| before the divide; 0 = unguarded         */
+    int32_t move_to_mantle;  /* 1 = offset ends on the mantle / cap rim (reference behaviour);
+                                0 = offset ends on the distance foot point (Projection.py:19 flag;
+                                the reference's own False branch is shape-broken, :110)               */
+    int32_t norm_fma;        /* which of ATen's two CPU roundings of norm() to mirror:
+                                0 = strided xyz axis (cylinder tensors from DataFrame.values, the
+                                    label_clouds / project_clouds path): sqrt((x*x + y*y) + z*z)
+                                1 = contiguous xyz axis (C-ordered tensors, QSMFittingDepthFirst.py:1039,
+                                    or M == 1): sqrt(fma(z,z, fma(y,y, x*x)))                         */
+    int32_t mode;            /* TM_MODE_*                                                             */
+    float   cell_size;       /* voxel edge in metres for TM_MODE_GRID; 0 = automatic                  */
+    int32_t reserved[2];     /* must be 0                                                             */
+} tm_params;
+
+/* Counters of the most recent tm_label_points / tm_label_cloud_host call (tm_get_stats syncs). */
+typedef struct tm_stats {
+    uint64_t pairs_evaluated;   /* exact (point, cylinder) distance evaluations, all kernels          */
+    uint64_t points_grid;       /* points answered by the voxel-tile kernel                           */
+    uint64_t points_brute;      /* points answered by the exhaustive kernel (outliers, brute mode)    */
+    uint64_t tile_entries;      /* sum of candidate-tile lengths built for occupied voxels            */
+    uint32_t voxels_occupied;   /* voxels holding at least one point                                  */
+    uint32_t voxels_brute;      /* occupied voxels routed to the exhaustive kernel                    */
+    uint32_t work_items;        /* (voxel, <=64-point slice) items processed by the tile kernel       */
+    uint32_t mode_used;         /* TM_MODE_BRUTE or TM_MODE_GRID                                      */
+    float    cell_size;         /* voxel edge actually used                                           */
+    uint32_t grid_dim[3];       /* voxel grid extent                                                  */
+} tm_stats;
+
+int tm_version(void);                                   /* returns TM_ABI_VERSION                     */
+int tm_create(int device, tm_handle **out);             /* fails with TM_ERR_CUDA if no such device   */
+int tm_destroy(tm_handle *h);
+const char *tm_last_error(const tm_handle *h);          /* valid until the next call on h             */
+const char *tm_status_string(int status);
+
+/*
+ * Cylinder preparation — replaces LabelGenerationCuda.py:121-123 / Projection.py:126-132:
+ *   axis = end - start;  axis_length = ||axis||;  axis_unit = axis / max(axis_length, axis_eps)
+ * start/end: (M,3) with element strides (row_stride, col_stride) — DataFrame.values tensors are
+ * Fortran-ordered, i.e. strides (1, M).  out_axis_length (M,), out_axis_unit (M,3) row-major.
+ * axis_eps: 0 (variant A) or 1e-8 (variant B).  norm_fma as in tm_params.
+ */
+int tm_prepare_cylinders(tm_handle *h,
+                         const float *start, int64_t start_row_stride, int64_t start_col_stride,
+                         const float *end, int64_t end_row_stride, int64_t end_col_stride,
+                         int64_t m, float axis_eps, int32_t norm_fma,
+                         float *out_axis_length, float *out_axis_unit, void *stream);
+
+/*
+ * Install the cylinder table (the cylinder arguments of closest_cylinder_cuda_batch,
+ * LabelGenerationCuda.py:20 / Projection.py:19).  The values are used exactly as given
+ * (axis_unit / axis_length are NOT recomputed).  Packs two float4 records per cylinder,
+ * computes solid-cylinder AABBs and bins them into the uniform voxel grid.
+ * ids may be NULL (then id == row index).  Synchronises `stream` (it sizes the grid on the host).
+ */
+int tm_set_cylinders(tm_handle *h,
+                     const float *start, int64_t start_row_stride, int64_t start_col_stride,
+                     const float *axis_unit, int64_t unit_row_stride, int64_t unit_col_stride,
+                     const float *axis_length, int64_t length_stride,
+                     const float *radius, int64_t radius_stride,
+                     const int32_t *ids, int64_t ids_stride,
+                     int64_t m, void *stream);
+
+/*
+ * closest_cylinder_cuda_batch for N device-resident points (LabelGenerationCuda.py:20-111,
+ * Projection.py:19-115).  pts: fp32, row i at pts + i*row_stride (elements), xyz contiguous.
+ * Outputs (any may be NULL): out_index (N,) winning ROW, out_id (N,) = ids[row] (:109),
+ * out_dist (N,) (:88), out_offset (N,3) row-major (:106), out_radius (N,) radius of the winner.
+ * N == 0 is a no-op.  M == 0 with N > 0 returns TM_ERR_NO_CYLINDERS.
+ */
+int tm_label_points(tm_handle *h, const float *pts, int64_t n, int64_t row_stride,
+                    const tm_params *params,
+                    int32_t *out_index, int32_t *out_id, float *out_dist, float *out_offset,
+                    float *out_radius, void *stream);
+
+/*
+ * The (N,7) float64 record [x, y, z, ox, oy, oz, ID] of generate_offset_cloud_cuda_batched
+ * (LabelGenerationCuda.py:114,131-133): xyz copied from the caller's cloud at ITS precision
+ * (cloud_dtype TM_F32 / TM_F64, row stride in elements), offsets and ids widened to float64.
+ */
+int tm_assemble_records(tm_handle *h, const void *cloud, int32_t cloud_dtype, int64_t n,
+                        int64_t cloud_row_stride, const float *offset, const int32_t *id,
+                        double *out_records, void *stream);
+
+/*
+ * generate_offset_cloud_cuda_batched end to end for a HOST cloud (LabelGenerationCuda.py:113-135,
+ * Projection.py:117-144): chunks the cloud, overlaps H2D copy / labelling / record assembly / D2H
+ * on internal streams, and writes the (N,7) float64 record to out_records_host.
+ * cloud_host: (N, >=3) TM_F32 or TM_F64, row stride in elements.  out_dist_host (N,) may be NULL.
+ * Host buffers may be pageable; pinned buffers avoid a staging copy.  Synchronous.
+ */
+int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t cloud_dtype, int64_t n,
+                        int64_t cloud_row_stride, const tm_params *params,
+                        double *out_records_host, float *out_dist_host);
+
+/* Counters of the last labelling call.  Synchronises the device. */
+int tm_get_stats(tm_handle *h, tm_stats *out);
+
+/*
+ * Per-phase device timing of tm_label_points (CUDA events recorded on the caller's stream between the
+ * phases; off by default).  tm_get_phase_ms synchronises and fills out[0..TM_PHASES):
+ *   [0] bin points into voxels   [1] voxel scan / compaction   [2] scatter into voxel order
+ *   [3] candidate-tile build     [4] tile evaluate + fused label/offset write
+ *   [5] exhaustive kernel (brute mode, or the grid's outliers)   [6] exhaustive finalize   [7] whole call
+ * Phases that did not run report 0.
+ */
+#define TM_PHASES 8
+int tm_set_profiling(tm_handle *h, int enabled);
+int tm_get_phase_ms(tm_handle *h, float *out_ms);
+
+/*
+ * FP32 FMA-pipe probe: dependent FFMA chains on every SM; reports lane-operations per second
+ * (one FFMA = one lane-op, the convention of SURVEY.md A.6).  Used by bench.py as the FP32
+ * roofline denominator because MEASURED_PEAKS.json has no FP32 entry.  Synchronous.
+ */
+int tm_measure_fp32_peak(tm_handle *h, double *lane_ops_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREEMORPH_NN_H */
