@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--cylinders", type=int, default=N_CYLINDERS)
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-brute", action="store_true", help="skip the exhaustive-kernel FP32 yard-stick")
+    ap.add_argument("--skip-e2e", action="store_true", help="skip the host-API end-to-end leg (profiling runs)")
     args = ap.parse_args()
     N_POINTS, N_CYLINDERS = args.points, args.cylinders
     if args.impl == "reference":
@@ -291,8 +292,8 @@ def main():
     # ---- end to end through the public host API: pinned host cloud in, pinned (N,7) float64 records out
     rec_pinned = torch.empty((N_POINTS, 7), dtype=torch.float64, pin_memory=True)
     rec_np, cloud_np = rec_pinned.numpy(), pinned_in.numpy()
-    e2e_steps = max(2, min(steps, 5))
-    for _ in range(2):
+    e2e_steps = 0 if args.skip_e2e else max(2, min(steps, 5))
+    for _ in range(0 if args.skip_e2e else 2):
         eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
     if world > 1:
         dist.barrier()
@@ -305,8 +306,8 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_POINTS * e2e_steps / float(te.item())
-    e2e_ok = bool((rec_np[:1000, 6] == out["id"][:1000].cpu().numpy()).all())
+    e2e_value = world * N_POINTS * e2e_steps / float(te.item()) if e2e_steps else None
+    e2e_ok = bool((rec_np[:1000, 6] == out["id"][:1000].cpu().numpy()).all()) if e2e_steps else None
 
     if rank != 0:
         if world > 1:

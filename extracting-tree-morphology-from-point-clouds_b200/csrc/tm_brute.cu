@@ -142,6 +142,46 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
     }
 }
 
+// Exhaustive search for a SHORT list of points (the grid path's outliers; the count lives on the device).
+// One warp per (point, 1024-cylinder chunk) task: the lanes stride over the chunk's records straight from
+// global memory (coalesced 512-byte requests, the table is L2 resident), keep a 64-bit (distance, index)
+// key each, and a five-step warp-shuffle butterfly reduces them with torch.argmin's comparator (NaN first,
+// then distance, then lowest index).  Chunks of one point meet in an atomicMin on the key.
+constexpr int WARP_CHUNK = 1024;
+
+template <bool GUARD, bool NFMA>
+__global__ void __launch_bounds__(256)
+brute_warp_kernel(const float *__restrict__ pts, int64_t row_stride, const int32_t *__restrict__ sel,
+                  const unsigned int *__restrict__ d_count, const float4 *__restrict__ recA,
+                  const float4 *__restrict__ recB, int m, float atol, float eps, unsigned long long *__restrict__ keys) {
+    const unsigned int n_eff = *d_count;
+    if (n_eff == 0) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nchunks = (static_cast<unsigned long long>(m) + WARP_CHUNK - 1) / WARP_CHUNK;
+    const unsigned long long total = static_cast<unsigned long long>(n_eff) * nchunks;
+    const unsigned long long nwarps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+    for (unsigned long long task = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; task < total;
+         task += nwarps) {
+        const unsigned int slot = static_cast<unsigned int>(task / nchunks);
+        const int chunk = static_cast<int>(task % nchunks);
+        const float *p = pts + static_cast<int64_t>(sel[slot]) * row_stride;
+        const float px = p[0], py = p[1], pz = p[2];
+        unsigned long long best = KEY_NONE;
+        const int j_end = min(m, (chunk + 1) * WARP_CHUNK);
+        for (int j = chunk * WARP_CHUNK + lane; j < j_end; j += 32) {
+            const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, recA[j], recB[j], atol, eps, nullptr);
+            const unsigned long long k = make_key(d, static_cast<uint32_t>(j));
+            best = k < best ? k : best;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if (lane == 0) atomicMin(keys + slot, best);
+    }
+}
+
 template <int P, bool GUARD, bool NFMA>
 static cudaError_t launch_brute(dim3 grid, cudaStream_t st, const float *pts, int64_t n, int64_t rs, const int32_t *sel,
                                 const unsigned int *d_count, const float4 *A, const float4 *B, int m, int tps, float atol,
@@ -161,13 +201,7 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
 
     int P, splits;
     int64_t nblk;
-    if (d_count) {
-        // the true count is only known on the device (outliers of the grid path, normally a handful):
-        // a fixed launch that strides over however many points there are, table split 32 ways
-        P = 1;
-        nblk = std::min<int64_t>((n_launch + BRUTE_THREADS - 1) / BRUTE_THREADS, h->sm_count);
-        splits = std::min(ntiles, 32);
-    } else {
+    {
         // points per thread: 2 once there are enough points to fill the machine twice over
         const int64_t full_wave = static_cast<int64_t>(h->sm_count) * 3 * BRUTE_THREADS;
         P = (n_launch >= 4 * full_wave) ? 2 : 1;
@@ -225,9 +259,33 @@ int label_brute(tm_handle *h, const LabelArgs &a) {
 int label_brute_subset(tm_handle *h, const LabelArgs &a, const int32_t *sel, const unsigned int *d_count,
                        unsigned int max_count) {
     if (max_count == 0) return TM_OK;
-    // the true count lives on the device; launch for a modest grid and let the kernel stride
-    const int64_t n_launch = std::min<int64_t>(max_count, a.n);
-    return run_brute(h, a, sel, d_count, n_launch);
+    // The true count lives on the device (normally a handful of points): a fixed launch of warps that
+    // stride over (point, chunk) tasks.  h->keys[slot] was set to KEY_NONE by whoever appended the slot.
+    const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
+    const int m = static_cast<int>(h->m);
+    const float4 *A = h->recA.as<float4>();
+    const float4 *B = h->recB.as<float4>();
+    unsigned long long *keys = h->keys.as<unsigned long long>();
+    const int wgrid = h->sm_count * 8;
+#define TM_WARP_CASE(G, F)                                                                                         \
+    brute_warp_kernel<G, F><<<wgrid, 256, 0, a.stream>>>(a.pts, a.row_stride, sel, d_count, A, B, m, a.prm.perp_atol, \
+                                                        a.prm.norm_eps, keys)
+    if (guard) { if (nfma) TM_WARP_CASE(true, true); else TM_WARP_CASE(true, false); }
+    else       { if (nfma) TM_WARP_CASE(false, true); else TM_WARP_CASE(false, false); }
+#undef TM_WARP_CASE
+    TM_CUDA(h, cudaGetLastError());
+    mark(h, 6, a.stream);
+    const int fgrid = h->sm_count * 4;
+#define TM_FIN_CASE(G, F)                                                                                          \
+    finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, sel, d_count, keys, A, B,          \
+                                                       h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
+                                                       a.prm.move_to_mantle, a.out_index, a.out_id, a.out_dist,     \
+                                                       a.out_offset, a.out_radius)
+    if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
+    else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
+#undef TM_FIN_CASE
+    TM_CUDA(h, cudaGetLastError());
+    return TM_OK;
 }
 
 }  // namespace tmn

@@ -325,6 +325,7 @@ constexpr uint32_t NO_CELL = 0xFFFFFFFFu;
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
                                                         uint32_t *__restrict__ cell_count, uint32_t *__restrict__ pt_cell,
                                                         uint32_t *__restrict__ pt_rank, int32_t *__restrict__ outlier_idx,
+                                                        unsigned long long *__restrict__ outlier_keys,
                                                         DevStats *__restrict__ st) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
             pt_cell[i] = NO_CELL;
             const unsigned int s = atomicAdd(&st->outliers, 1u);
             outlier_idx[s] = static_cast<int32_t>(i);
+            outlier_keys[s] = KEY_NONE;
         }
     }
 }
@@ -424,6 +426,7 @@ struct TileBuildArgs {
     uint32_t pool_entries;
     uint4 *items;
     int32_t *outlier_idx;
+    unsigned long long *outlier_keys;
     DevStats *st;
 };
 
@@ -545,7 +548,10 @@ __global__ void __launch_bounds__(TB_WARPS * 32) tile_build_kernel(TileBuildArgs
             unsigned int base = 0;
             if (lane == 0) { base = atomicAdd(&a.st->outliers, pcount); atomicAdd(&a.st->voxels_brute, 1u); }
             base = __shfl_sync(0xffffffffu, base, 0);
-            for (uint32_t i = lane; i < pcount; i += 32) a.outlier_idx[base + i] = __float_as_int(a.sorted[pstart + i].w);
+            for (uint32_t i = lane; i < pcount; i += 32) {
+                a.outlier_idx[base + i] = __float_as_int(a.sorted[pstart + i].w);
+                a.outlier_keys[base + i] = KEY_NONE;
+            }
         }
         __syncwarp();
     }
@@ -734,6 +740,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     TM_CUDA(h, h->tile_meta.ensure(sizeof(uint32_t) * max_occ));
     TM_CUDA(h, h->items.ensure(sizeof(uint4) * max_items));
     TM_CUDA(h, h->outlier_idx.ensure(sizeof(int32_t) * n));
+    TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * n));
     TM_CUDA(h, h->tileA.ensure(sizeof(float4) * pool));
     TM_CUDA(h, h->tileB.ensure(sizeof(float4) * pool));
     TM_CUDA(h, h->tileI.ensure(sizeof(int32_t) * pool));
@@ -747,7 +754,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
     bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cell_count.as<uint32_t>(),
                                                 h->pt_cell.as<uint32_t>(), h->pt_rank.as<uint32_t>(),
-                                                h->outlier_idx.as<int32_t>(), dst);
+                                                h->outlier_idx.as<int32_t>(), h->keys.as<unsigned long long>(), dst);
     TM_CUDA(h, cudaGetLastError());
     mark(h, 1, st);
     int rc = run_scan(h, h->cell_count.as<uint32_t>(), ncodes, 1, h->cell_start.as<uint32_t>(), h->occ_cells.as<uint32_t>(),
@@ -776,6 +783,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     tb.pool_entries = static_cast<uint32_t>(pool);
     tb.items = h->items.as<uint4>();
     tb.outlier_idx = h->outlier_idx.as<int32_t>();
+    tb.outlier_keys = h->keys.as<unsigned long long>();
     tb.st = dst;
     const int tb_blocks = static_cast<int>(std::min<size_t>((max_occ + TB_WARPS - 1) / TB_WARPS, static_cast<size_t>(h->sm_count) * 8));
     tile_build_kernel<<<tb_blocks, TB_WARPS * 32, 0, st>>>(tb, g);

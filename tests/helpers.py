@@ -51,10 +51,15 @@ def assert_parity(got: dict, ora: dict, what: str = "", require_bitwise: bool = 
     nan_g, nan_o = np.isnan(got["dist"]), np.isnan(ora["dist"])
     assert (nan_g == nan_o).all(), f"{what}: NaN pattern of distances differs"
     fin = ~nan_o
-    dd = np.abs(got["dist"][fin].astype(np.float64) - ora["dist"][fin])
+    with np.errstate(invalid="ignore"):
+        gd, od = got["dist"][fin].astype(np.float64), ora["dist"][fin].astype(np.float64)
+        dd = np.where(gd == od, 0.0, np.abs(gd - od))             # equal infinities count as equal
     assert dd.size == 0 or dd.max() <= ABS_TOL_M, f"{what}: distance differs by {dd.max():.3g} m"
     ok_rows = idx_ok & fin
-    do = np.abs(got["offset"][ok_rows].astype(np.float64) - ora["offset"][ok_rows])
+    with np.errstate(invalid="ignore"):
+        go, oo = got["offset"][ok_rows].astype(np.float64), ora["offset"][ok_rows].astype(np.float64)
+        do = np.where(go == oo, 0.0, np.abs(go - oo))
+    assert (np.isnan(go) == np.isnan(oo)).all(), f"{what}: NaN pattern of offsets differs"
     do = do[~np.isnan(do)]
     assert do.size == 0 or do.max() <= ABS_TOL_M, f"{what}: offset differs by {do.max():.3g} m"
     if require_bitwise:
