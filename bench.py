@@ -317,7 +317,7 @@ def main():
     # ---- rooflines
     hbm_peak, peak_kind = load_peaks()
     fp32_peak = eng.fp32_peak()
-    dom = max(("evaluate", "exhaustive", "bin", "scatter", "tile_build", "scan"), key=lambda k: phases.get(k, 0.0))
+    dom = max(("evaluate", "ring", "exhaustive", "finalize", "bin", "scatter", "scan", "unpack"), key=lambda k: phases.get(k, 0.0))
     dom_ms = phases.get(dom, 0.0) or ms_per_step
     achieved_gbs = BYTES_PER_POINT * N_POINTS / (dom_ms * 1e-3) / 1e9
     pairs = stats["pairs_evaluated"]

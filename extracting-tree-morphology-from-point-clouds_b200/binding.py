@@ -13,9 +13,9 @@ from . import build as _build
 TM_OK, TM_ERR_INVALID, TM_ERR_NO_CYLINDERS, TM_ERR_CUDA, TM_ERR_NOMEM, TM_ERR_STATE = range(6)
 TM_MODE_AUTO, TM_MODE_BRUTE, TM_MODE_GRID = 0, 1, 2
 TM_F32, TM_F64 = 0, 1
-ABI_VERSION = 1
-TM_PHASES = 8
-PHASE_NAMES = ("bin", "scan", "scatter", "tile_build", "evaluate", "exhaustive", "exhaustive_finalize", "total")
+ABI_VERSION = 2
+TM_PHASES = 9
+PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "ring", "exhaustive", "finalize", "unpack", "total")
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 
@@ -26,10 +26,11 @@ class TmParams(ctypes.Structure):
 
 
 class TmStats(ctypes.Structure):
-    _fields_ = [("pairs_evaluated", ctypes.c_uint64), ("points_grid", ctypes.c_uint64),
-                ("points_brute", ctypes.c_uint64), ("tile_entries", ctypes.c_uint64),
-                ("voxels_occupied", ctypes.c_uint32), ("voxels_brute", ctypes.c_uint32),
-                ("work_items", ctypes.c_uint32), ("mode_used", ctypes.c_uint32), ("cell_size", c_f32),
+    _fields_ = [("pairs_evaluated", ctypes.c_uint64), ("cull_tests", ctypes.c_uint64),
+                ("points_grid", ctypes.c_uint64), ("points_ring", ctypes.c_uint64),
+                ("points_brute", ctypes.c_uint64), ("index_entries", ctypes.c_uint64),
+                ("voxels_occupied", ctypes.c_uint32), ("work_items", ctypes.c_uint32),
+                ("mode_used", ctypes.c_uint32), ("cell_size", c_f32), ("reach", c_f32),
                 ("grid_dim", ctypes.c_uint32 * 3)]
 
     def as_dict(self) -> dict:

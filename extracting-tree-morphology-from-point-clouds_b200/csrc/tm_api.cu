@@ -51,7 +51,7 @@ __global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64
                             const float *__restrict__ radius, int64_t r_s, const int32_t *__restrict__ ids, int64_t i_s,
                             int m, float4 *__restrict__ recA, float4 *__restrict__ recB, int32_t *__restrict__ out_ids,
                             float4 *__restrict__ boxlo, float4 *__restrict__ boxhi, int *__restrict__ bbox,
-                            int32_t *__restrict__ special) {
+                            int32_t *__restrict__ special, int32_t *__restrict__ aligned) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const float sx = start[c * s_rs], sy = start[c * s_rs + s_cs], sz = start[c * s_rs + 2 * s_cs];
@@ -63,7 +63,8 @@ __global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64
     const bool finite = isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(ux) && isfinite(uy) && isfinite(uz) &&
                         isfinite(len) && isfinite(rad);
     const float un = ux * ux + uy * uy + uz * uz;
-    const bool unit_ok = fabsf(un - 1.f) <= 1e-3f || (un == 0.f && len == 0.f);
+    // the capsule bound of tm_eval.cuh needs a unit axis: a correctly normalised fp32 vector is within 4e-7
+    const bool unit_ok = fabsf(un - 1.f) <= 4e-6f || (un == 0.f && len == 0.f);
     if (!finite || !unit_ok || len < 0.f) {
         boxlo[c] = make_float4(0.f, 0.f, 0.f, 1.f);
         boxhi[c] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -84,6 +85,8 @@ __global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64
     atomicMin(&bbox[0], float_to_ordered(lx)); atomicMin(&bbox[1], float_to_ordered(ly)); atomicMin(&bbox[2], float_to_ordered(lz));
     atomicMax(&bbox[3], float_to_ordered(hx)); atomicMax(&bbox[4], float_to_ordered(hy)); atomicMax(&bbox[5], float_to_ordered(hz));
     atomicAdd(&bbox[7], 1);
+    // axis-parallel (two exactly-zero unit components): NaN for every point on the axis line in variant A
+    if ((ux == 0.f) + (uy == 0.f) + (uz == 0.f) >= 2) aligned[atomicAdd(&bbox[8], 1)] = c;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -177,10 +180,10 @@ int tm_destroy(tm_handle *h) {
     if (!h) return TM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_list,
-                          &h->long_list, &h->special, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count, &h->cell_start,
-                          &h->block_sums, &h->sorted_pts, &h->occ_cells, &h->tile_meta, &h->tileA, &h->tileB, &h->tileI,
-                          &h->items, &h->outlier_idx, &h->dstats, &h->scratch_f};
+    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
+                          &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
+                          &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
+                          &h->pend_idx, &h->brute_slots, &h->rec, &h->dstats, &h->scratch_f};
     for (auto *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         h->chunk_in[i].release(); h->chunk_rec[i].release(); h->chunk_off[i].release(); h->chunk_id[i].release();
@@ -223,7 +226,7 @@ int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_c
     h->m = m;
     h->have_cyl = true;
     h->have_grid = false;
-    h->n_special = h->n_long = h->n_listed = 0;
+    h->n_special = h->n_long = h->n_listed = h->n_aligned = 0;
     if (m == 0) return TM_OK;
     const size_t mm = static_cast<size_t>(m);
     TM_CUDA(h, h->recA.ensure(sizeof(float4) * mm));
@@ -232,15 +235,17 @@ int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_c
     TM_CUDA(h, h->boxlo.ensure(sizeof(float4) * mm));
     TM_CUDA(h, h->boxhi.ensure(sizeof(float4) * mm));
     TM_CUDA(h, h->special.ensure(sizeof(int32_t) * mm));
-    TM_CUDA(h, h->bbox.ensure(sizeof(int) * 8));
-    const int init[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, static_cast<int>(0x80000000), static_cast<int>(0x80000000),
-                         static_cast<int>(0x80000000), 0, 0};
+    TM_CUDA(h, h->aligned.ensure(sizeof(int32_t) * mm));
+    TM_CUDA(h, h->bbox.ensure(sizeof(int) * 10));
+    // [0..2] min corner, [3..5] max corner (ordered ints), [6] special, [7] regular, [8] axis-parallel
+    const int init[10] = {0x7fffffff, 0x7fffffff, 0x7fffffff, static_cast<int>(0x80000000), static_cast<int>(0x80000000),
+                          static_cast<int>(0x80000000), 0, 0, 0, 0};
     TM_CUDA(h, cudaMemcpyAsync(h->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const int blocks = static_cast<int>((m + 127) / 128);
     pack_kernel<<<blocks, 128, 0, st>>>(start, s_rs, s_cs, unit, u_rs, u_cs, length, l_s, radius, r_s, ids, i_s,
                                         static_cast<int>(m), h->recA.as<float4>(), h->recB.as<float4>(), h->ids.as<int32_t>(),
                                         h->boxlo.as<float4>(), h->boxhi.as<float4>(), h->bbox.as<int>(),
-                                        h->special.as<int32_t>());
+                                        h->special.as<int32_t>(), h->aligned.as<int32_t>());
     TM_CUDA(h, cudaGetLastError());
     TM_CUDA(h, cudaStreamSynchronize(st));      // `init` is a stack buffer; also surfaces bad input pointers here
     return TM_OK;
@@ -284,6 +289,7 @@ int tm_label_points(tm_handle *h, const float *pts, int64_t n, int64_t row_strid
     h->stats = tm_stats{};
     LabelArgs a{pts, n, row_stride, *params, out_index, out_id, out_dist, out_offset, out_radius,
                 static_cast<cudaStream_t>(stream)};
+    h->last_n = n;
     for (bool &b : h->phase_hit) b = false;
     mark(h, 0, a.stream);
     rc = label_dispatch(h, a);
@@ -414,6 +420,7 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         total.pairs_evaluated += h->stats.pairs_evaluated;
         total.points_brute += h->stats.points_brute;
         total.mode_used = h->stats.mode_used;
+        h->last_n = cnt;
         rc = tm_assemble_records(h, h->chunk_in[b].p, dtype, cnt, row_stride, h->chunk_off[b].as<float>(),
                                  h->chunk_id[b].as<int32_t>(), h->chunk_rec[b].as<double>(), s_cmp);
         if (rc != TM_OK) return rc;
@@ -447,17 +454,19 @@ int tm_get_stats(tm_handle *h, tm_stats *out) {
     TM_CUDA(h, cudaSetDevice(h->device));
     TM_CUDA(h, cudaDeviceSynchronize());
     tm_stats s = h->stats;
-    if (s.mode_used == TM_MODE_GRID && h->dstats.p) {
+    if (s.mode_used == TM_MODE_GRID && h->dstats.p && h->n_listed + h->n_long > 0) {
         tmn::DevStats d;
         TM_CUDA(h, cudaMemcpy(&d, h->dstats.p, sizeof(d), cudaMemcpyDeviceToHost));
-        s.pairs_evaluated += d.pairs_grid + static_cast<uint64_t>(d.outliers) * static_cast<uint64_t>(h->m);
-        s.points_grid = s.points_grid >= d.outliers ? s.points_grid - d.outliers : 0;   // label_grid stored N here
-        s.points_brute += d.outliers;
-        s.tile_entries = d.tile_entries;
+        s.pairs_evaluated += d.pairs_grid + d.pairs_ring;
+        s.cull_tests += d.cull_tests;
+        s.points_grid += static_cast<uint64_t>(h->last_n) - d.pending;
+        s.points_ring += d.pending - d.n_brute;
+        s.points_brute += d.n_brute;
+        s.index_entries = h->index_entries;
         s.voxels_occupied = d.voxels_occupied;
-        s.voxels_brute = d.voxels_brute;
         s.work_items = d.work_items;
         s.cell_size = h->grid.h;
+        s.reach = h->reach;
         s.grid_dim[0] = static_cast<uint32_t>(h->grid.nx);
         s.grid_dim[1] = static_cast<uint32_t>(h->grid.ny);
         s.grid_dim[2] = static_cast<uint32_t>(h->grid.nz);
@@ -478,15 +487,15 @@ int tm_get_phase_ms(tm_handle *h, float *out_ms) {
     if (!h->profiling || !h->phase_hit[0] || !h->phase_hit[9]) return TM_OK;
     TM_CUDA(h, cudaSetDevice(h->device));
     TM_CUDA(h, cudaEventSynchronize(h->phase_ev[9]));
-    // phase p spans mark p -> the next mark that was recorded
-    for (int p = 0; p < 7; ++p) {
-        if (!h->phase_hit[p] ) continue;
+    // phase p spans mark p -> the next mark that was recorded (mark 9 = end of the call)
+    for (int p = 0; p < 8; ++p) {
+        if (!h->phase_hit[p]) continue;
         int q = p + 1;
         while (q < 9 && !h->phase_hit[q]) ++q;
         if (p == 0 && !h->phase_hit[1]) continue;          // brute mode has no binning phase
         TM_CUDA(h, cudaEventElapsedTime(&out_ms[p], h->phase_ev[p], h->phase_ev[q]));
     }
-    TM_CUDA(h, cudaEventElapsedTime(&out_ms[7], h->phase_ev[0], h->phase_ev[9]));
+    TM_CUDA(h, cudaEventElapsedTime(&out_ms[8], h->phase_ev[0], h->phase_ev[9]));
     return TM_OK;
 }
 

@@ -121,11 +121,11 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
                 const float4 *__restrict__ recA, const float4 *__restrict__ recB, const int32_t *__restrict__ ids,
                 float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index,
                 int32_t *__restrict__ out_id, float *__restrict__ out_dist, float *__restrict__ out_offset,
-                float *__restrict__ out_radius) {
+                float *__restrict__ out_radius, float4 *__restrict__ rec) {
     const int64_t n_eff = d_count ? static_cast<int64_t>(*d_count) : n;
     for (int64_t slot = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; slot < n_eff;
          slot += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t row = sel ? static_cast<int64_t>(sel[slot]) : slot;
+        const int64_t row = sel ? static_cast<int64_t>(sel[slot] & 0x7fffffff) : slot;   // sign bit: "outside the grid" flag
         const uint32_t j = key_index(keys[slot]);
         const float *p = pts + row * row_stride;
         const float px = p[0], py = p[1], pz = p[2];
@@ -134,6 +134,7 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
         eval_pair<GUARD, NFMA, true>(px, py, pz, a, b, atol, eps, &g);
         float ox, oy, oz;
         mantle_offset<NFMA>(g, px, py, pz, move_to_mantle != 0, ox, oy, oz);
+        if (rec) { store_record(rec, row, j, ids[j], g.dist, ox, oy, oz, b.w); continue; }
         if (out_index) out_index[row] = static_cast<int32_t>(j);
         if (out_id) out_id[row] = ids[j];
         if (out_dist) out_dist[row] = g.dist;
@@ -142,43 +143,98 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
     }
 }
 
-// Exhaustive search for a SHORT list of points (the grid path's outliers; the count lives on the device).
-// One warp per (point, 1024-cylinder chunk) task: the lanes stride over the chunk's records straight from
-// global memory (coalesced 512-byte requests, the table is L2 resident), keep a 64-bit (distance, index)
-// key each, and a five-step warp-shuffle butterfly reduces them with torch.argmin's comparator (NaN first,
-// then distance, then lowest index).  Chunks of one point meet in an atomicMin on the key.
+// Exhaustive search for the SHORT list of pending points the voxel tiles and the ring search could not certify
+// (outside the grid, non-finite, farther than RING_MAX shells from every cylinder; the count lives on the device).
+// One warp per (point, 1024-cylinder chunk) task: the lanes stride over the chunk's records straight from global
+// memory (coalesced 512-byte requests, the table is L2 resident), skip candidates whose capsule lies beyond the
+// incumbent (same cull as the tile kernel, with a per-point rounding allowance), keep a 64-bit (distance, index)
+// key each, and a five-step warp-shuffle butterfly reduces them with torch.argmin's comparator (NaN first, then
+// distance, then lowest index).  Chunks of one point meet in an atomicMin on the key.  The warp that owns chunk 0
+// also evaluates the cylinders the cull cannot bound (special) and the axis-parallel ones (variant A).
 constexpr int WARP_CHUNK = 1024;
 
+struct BruteCullArgs {
+    const float *pts;
+    int64_t row_stride;
+    const int32_t *pend_idx;
+    const uint32_t *brute_slots;
+    const unsigned int *d_count;
+    const float4 *recA, *recB;
+    int m;
+    const int32_t *special, *aligned;
+    uint32_t n_special, n_aligned;
+    float atol, eps, maxabs;
+    unsigned long long *keys;
+    DevStats *st;
+};
+
 template <bool GUARD, bool NFMA>
-__global__ void __launch_bounds__(256)
-brute_warp_kernel(const float *__restrict__ pts, int64_t row_stride, const int32_t *__restrict__ sel,
-                  const unsigned int *__restrict__ d_count, const float4 *__restrict__ recA,
-                  const float4 *__restrict__ recB, int m, float atol, float eps, unsigned long long *__restrict__ keys) {
-    const unsigned int n_eff = *d_count;
+__global__ void __launch_bounds__(256) brute_cull_kernel(BruteCullArgs a) {
+    const unsigned int n_eff = *a.d_count;
     if (n_eff == 0) return;
     const int lane = threadIdx.x & 31;
-    const unsigned long long nchunks = (static_cast<unsigned long long>(m) + WARP_CHUNK - 1) / WARP_CHUNK;
+    const unsigned long long nchunks = (static_cast<unsigned long long>(a.m) + WARP_CHUNK - 1) / WARP_CHUNK;
     const unsigned long long total = static_cast<unsigned long long>(n_eff) * nchunks;
     const unsigned long long nwarps = (static_cast<unsigned long long>(gridDim.x) * blockDim.x) >> 5;
+    unsigned long long pairs = 0, culls = 0;
     for (unsigned long long task = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; task < total;
          task += nwarps) {
-        const unsigned int slot = static_cast<unsigned int>(task / nchunks);
+        const unsigned int slot = a.brute_slots[static_cast<unsigned int>(task / nchunks)];
         const int chunk = static_cast<int>(task % nchunks);
-        const float *p = pts + static_cast<int64_t>(sel[slot]) * row_stride;
+        const float *p = a.pts + static_cast<int64_t>(a.pend_idx[slot] & 0x7fffffff) * a.row_stride;
         const float px = p[0], py = p[1], pz = p[2];
+        // rounding allowance at this point's own coordinate scale (inf / NaN coordinates: nothing is culled)
+        const float slack = 1e-4f + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
+        const unsigned long long key0 = a.keys[slot];          // incumbent from the ring search / other chunks (may be stale)
         unsigned long long best = KEY_NONE;
-        const int j_end = min(m, (chunk + 1) * WARP_CHUNK);
+        float thr = thr_of(key0, slack);
+        if (!(fabsf(px) + fabsf(py) + fabsf(pz) < 3.0e38f)) thr = __int_as_float(0x7fc00000);
+        const int j_end = min(a.m, (chunk + 1) * WARP_CHUNK);
         for (int j = chunk * WARP_CHUNK + lane; j < j_end; j += 32) {
-            const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, recA[j], recB[j], atol, eps, nullptr);
-            const unsigned long long k = make_key(d, static_cast<uint32_t>(j));
-            best = k < best ? k : best;
+            const float4 ca = a.recA[j], cb = a.recB[j];
+            if (cull_pass(px, py, pz, ca, cb, thr)) {
+                const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr);
+                const unsigned long long k = make_key(d, static_cast<uint32_t>(j));
+                best = k < best ? k : best;
+                thr = thr_of(best < key0 ? best : key0, slack);
+                ++pairs;
+            }
+            ++culls;
+        }
+        if (chunk == 0) {
+            for (uint32_t e = lane; e < a.n_special; e += 32) {
+                const uint32_t j = static_cast<uint32_t>(a.special[e]);
+                const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(px, py, pz, a.recA[j], a.recB[j], a.atol, a.eps, nullptr), j);
+                best = k < best ? k : best;
+                ++pairs;
+            }
+            if (!GUARD) {
+                for (uint32_t e = lane; e < a.n_aligned; e += 32) {
+                    const uint32_t j = static_cast<uint32_t>(a.aligned[e]);
+                    const float4 ca = a.recA[j], cb = a.recB[j];
+                    if (on_axis_line(px, py, pz, ca, cb)) {
+                        const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr), j);
+                        best = k < best ? k : best;
+                        ++pairs;
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
             best = other < best ? other : best;
         }
-        if (lane == 0) atomicMin(keys + slot, best);
+        if (lane == 0 && best != KEY_NONE) atomicMin(a.keys + slot, best);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        culls += __shfl_xor_sync(0xffffffffu, culls, o);
+    }
+    if (lane == 0 && (pairs | culls)) {
+        atomicAdd(&a.st->pairs_ring, pairs);
+        atomicAdd(&a.st->cull_tests, culls);
     }
 }
 
@@ -239,7 +295,7 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
     finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, n_launch, a.row_stride, sel, d_count, keys, A, B,     \
                                                        h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
                                                        a.prm.move_to_mantle, a.out_index, a.out_id, a.out_dist,     \
-                                                       a.out_offset, a.out_radius)
+                                                       a.out_offset, a.out_radius, nullptr)
     if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
     else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
 #undef TM_FIN_CASE
@@ -256,35 +312,38 @@ int label_brute(tm_handle *h, const LabelArgs &a) {
     return TM_OK;
 }
 
-int label_brute_subset(tm_handle *h, const LabelArgs &a, const int32_t *sel, const unsigned int *d_count,
-                       unsigned int max_count) {
-    if (max_count == 0) return TM_OK;
-    // The true count lives on the device (normally a handful of points): a fixed launch of warps that
-    // stride over (point, chunk) tasks.  h->keys[slot] was set to KEY_NONE by whoever appended the slot.
+int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, float slack, float maxabs) {
+    (void)slack;
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
-    const int m = static_cast<int>(h->m);
-    const float4 *A = h->recA.as<float4>();
-    const float4 *B = h->recB.as<float4>();
-    unsigned long long *keys = h->keys.as<unsigned long long>();
+    BruteCullArgs b;
+    b.pts = a.pts; b.row_stride = a.row_stride;
+    b.pend_idx = h->pend_idx.as<int32_t>();
+    b.brute_slots = h->brute_slots.as<uint32_t>();
+    b.d_count = &dst->n_brute;
+    b.recA = h->recA.as<float4>(); b.recB = h->recB.as<float4>();
+    b.m = static_cast<int>(h->m);
+    b.special = h->special.as<int32_t>(); b.aligned = h->aligned.as<int32_t>();
+    b.n_special = h->n_special; b.n_aligned = h->n_aligned;
+    b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = maxabs;
+    b.keys = h->keys.as<unsigned long long>();
+    b.st = dst;
     const int wgrid = h->sm_count * 8;
-#define TM_WARP_CASE(G, F)                                                                                         \
-    brute_warp_kernel<G, F><<<wgrid, 256, 0, a.stream>>>(a.pts, a.row_stride, sel, d_count, A, B, m, a.prm.perp_atol, \
-                                                        a.prm.norm_eps, keys)
-    if (guard) { if (nfma) TM_WARP_CASE(true, true); else TM_WARP_CASE(true, false); }
-    else       { if (nfma) TM_WARP_CASE(false, true); else TM_WARP_CASE(false, false); }
-#undef TM_WARP_CASE
-    TM_CUDA(h, cudaGetLastError());
+    if (guard) { if (nfma) brute_cull_kernel<true, true><<<wgrid, 256, 0, a.stream>>>(b); else brute_cull_kernel<true, false><<<wgrid, 256, 0, a.stream>>>(b); }
+    else       { if (nfma) brute_cull_kernel<false, true><<<wgrid, 256, 0, a.stream>>>(b); else brute_cull_kernel<false, false><<<wgrid, 256, 0, a.stream>>>(b); }
+    TM_KCHECK(h, a.stream, "brute_cull_kernel");
     mark(h, 6, a.stream);
-    const int fgrid = h->sm_count * 4;
+    // winner-only epilogue of EVERY pending slot (ring-certified and exhaustive alike) into the record buffer
+    const int fgrid = h->sm_count * 8;
 #define TM_FIN_CASE(G, F)                                                                                          \
-    finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, sel, d_count, keys, A, B,          \
+    finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, h->pend_idx.as<int32_t>(), &dst->pending,  \
+                                                       h->keys.as<unsigned long long>(), b.recA, b.recB,            \
                                                        h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
-                                                       a.prm.move_to_mantle, a.out_index, a.out_id, a.out_dist,     \
-                                                       a.out_offset, a.out_radius)
+                                                       a.prm.move_to_mantle, nullptr, nullptr, nullptr, nullptr,    \
+                                                       nullptr, h->rec.as<float4>())
     if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
     else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
 #undef TM_FIN_CASE
-    TM_CUDA(h, cudaGetLastError());
+    TM_KCHECK(h, a.stream, "finalize_kernel (pending)");
     return TM_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/treemorph_nn.h"
@@ -46,15 +47,15 @@ struct GridDesc {
 
 // device-side counters of one labelling call (mirrors tm_stats where it is data dependent)
 struct DevStats {
-    unsigned long long pairs_grid;
-    unsigned long long tile_entries;
-    unsigned long long points_grid;
+    unsigned long long pairs_grid;   // full evaluations in the voxel-tile kernel
+    unsigned long long pairs_ring;   // full evaluations in the ring-search and exhaustive-with-cull kernels
+    unsigned long long cull_tests;   // capsule lower-bound tests, all kernels
+    unsigned long long points_binned;
     unsigned int voxels_occupied;
-    unsigned int voxels_brute;
     unsigned int work_items;
-    unsigned int outliers;          // points routed to the exhaustive kernel
-    unsigned int tile_pool_used;    // entries (multiple of 4 per tile)
-    unsigned int pad;
+    unsigned int pending;            // points the voxel-tile kernel could not certify (slots of pend_idx / keys)
+    unsigned int n_brute;            // of those, points that need the exhaustive kernel (slots of brute_slots)
+    unsigned int pad[2];
 };
 
 }  // namespace tmn
@@ -72,30 +73,32 @@ struct tm_handle {
     tmn::DevBuf boxlo, boxhi;        // float4[M]: solid-cylinder AABB (w unused)
     tmn::DevBuf bbox;                // 6 floats as ordered ints: global min/max + counters
 
-    // ---- static voxel index of the cylinders ----
+    // ---- static voxel index of the cylinders (per table and cell size) ----
     bool have_grid = false;
-    float grid_cell = 0.f;          // cell size the index was built with
+    float grid_cell = 0.f;          // cell size the index was requested with
+    float reach = 0.f;              // certified radius D: list(V) holds every cylinder within D of voxel V
+    float maxabs = 0.f;             // largest |coordinate| of the grid (scales the rounding slack)
     tmn::GridDesc grid{};
-    tmn::DevBuf cyl_cell_start;      // uint32[ncell_codes + 1]: CSR offsets of the home lists
-    tmn::DevBuf cyl_cell_list;       // int32[]: cylinder rows per voxel
-    tmn::DevBuf long_list;           // int32[]: cylinders whose AABB spans too many voxels
-    tmn::DevBuf special;             // int32[]: non-finite cylinders, evaluated for every point
-    uint32_t n_long = 0, n_special = 0, n_listed = 0;
-    uint64_t cyl_list_len = 0;
+    tmn::DevBuf cyl_cell_start;      // uint32[ncell_codes + 1]: first pool entry of each voxel's tile (multiple of 4)
+    tmn::DevBuf cyl_cell_cnt;        // uint32[ncell_codes]: tile length
+    tmn::DevBuf tileA, tileB, tileI; // tile pool: packed records + cylinder row of every (voxel, cylinder) entry
+    tmn::DevBuf long_list;           // int32[]: cylinders whose dilated AABB spans too many voxels
+    tmn::DevBuf special;             // int32[]: non-finite / non-unit cylinders, evaluated for every point
+    tmn::DevBuf aligned;             // int32[]: axis-parallel cylinders (variant A: NaN for points on their axis LINE)
+    uint32_t n_long = 0, n_special = 0, n_listed = 0, n_aligned = 0;
+    uint64_t index_entries = 0;
 
     // ---- per-call scratch ----
-    tmn::DevBuf keys;                // u64 per point (brute) / per outlier
+    tmn::DevBuf keys;                // u64 per point (brute mode) / per pending slot (grid mode)
     tmn::DevBuf pt_cell, pt_rank;    // uint32 per point
     tmn::DevBuf cell_count, cell_start, block_sums;
     tmn::DevBuf sorted_pts;          // float4 per point {x,y,z,bits(original row)}
-    tmn::DevBuf occ_cells;           // uint32 per occupied voxel
-    tmn::DevBuf tile_meta;           // uint4 per occupied voxel
-    tmn::DevBuf tileA, tileB, tileI; // candidate tile pool
     tmn::DevBuf items;               // uint4 per work item
-    tmn::DevBuf outlier_idx;         // int32 original rows routed to the exhaustive kernel
+    tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)
+    tmn::DevBuf brute_slots;         // uint32 pending slots that need the exhaustive kernel
+    tmn::DevBuf rec;                 // 2 x float4 per point: {row index, id, dist, ox} {oy, oz, radius, 0}
     tmn::DevBuf dstats;              // tmn::DevStats + cursors
-    tmn::DevBuf scratch_f;           // misc float scratch (strided-input staging)
-    size_t tile_pool_entries = 0;
+    tmn::DevBuf scratch_f;           // misc float scratch
 
     // ---- host pipeline (tm_label_cloud_host) ----
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
@@ -111,6 +114,7 @@ struct tm_handle {
     bool phase_hit[10] = {false};
 
     tm_stats stats{};
+    int64_t last_n = 0;             // point count of the most recent labelling call (for tm_get_stats)
 };
 
 namespace tmn {
@@ -128,6 +132,20 @@ inline int fail(tm_handle *h, int code, const char *fmt, const char *a = "", con
                             "%s failed: %s", #expr, cudaGetErrorString(_e));                     \
         }                                                                                        \
     } while (0)
+
+// after a kernel launch: launch errors always; with TM_DEBUG_SYNC=1 in the environment also execution errors,
+// attributed to the kernel that raised them
+#define TM_KCHECK(h, st, name)                                                                   \
+    do {                                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e == cudaSuccess && tmn::debug_sync()) _e = cudaStreamSynchronize(st);              \
+        if (_e != cudaSuccess) return tmn::fail((h), TM_ERR_CUDA, "%s: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+inline bool debug_sync() {
+    static const bool on = [] { const char *e = getenv("TM_DEBUG_SYNC"); return e && e[0] == '1'; }();
+    return on;
+}
 
 // phase marks: event i is recorded when phase i-1 ends / phase i begins (0 = call start, 9 = call end)
 inline void mark(tm_handle *h, int i, cudaStream_t st) {
@@ -152,9 +170,9 @@ struct LabelArgs {
 
 // tm_brute.cu
 int label_brute(tm_handle *h, const LabelArgs &a);
-// exhaustive search for a subset of points given by original row indices (device array, count on device)
-int label_brute_subset(tm_handle *h, const LabelArgs &a, const int32_t *sel, const unsigned int *d_count,
-                       unsigned int max_count);
+// grid mode, after the voxel-tile and ring kernels: exhaustive search (with the capsule cull) for the pending
+// slots listed in h->brute_slots, then the winner-only epilogue for EVERY pending slot into h->rec
+int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, float slack, float maxabs);
 // tm_grid.cu
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream);
 int label_grid(tm_handle *h, const LabelArgs &a);

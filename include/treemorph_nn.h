@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TM_ABI_VERSION 1
+#define TM_ABI_VERSION 2
 
 /* status codes */
 #define TM_OK               0
@@ -47,7 +47,7 @@ extern "C" {
 /* tm_params.mode */
 #define TM_MODE_AUTO  0         /* grid when N*M is large enough to pay for it, else brute force      */
 #define TM_MODE_BRUTE 1         /* exhaustive tiled kernel: every (point, cylinder) pair              */
-#define TM_MODE_GRID  2         /* voxel-binned points + per-voxel candidate tiles (exact pruning)    */
+#define TM_MODE_GRID  2         /* voxel-binned points + per-voxel cylinder tiles (exact pruning)     */
 
 /* cloud element types for the host/record entry points */
 #define TM_F32 0
@@ -78,16 +78,18 @@ typedef struct tm_params {
 
 /* Counters of the most recent tm_label_points / tm_label_cloud_host call (tm_get_stats syncs). */
 typedef struct tm_stats {
-    uint64_t pairs_evaluated;   /* exact (point, cylinder) distance evaluations, all kernels          */
-    uint64_t points_grid;       /* points answered by the voxel-tile kernel                           */
-    uint64_t points_brute;      /* points answered by the exhaustive kernel (outliers, brute mode)    */
-    uint64_t tile_entries;      /* sum of candidate-tile lengths built for occupied voxels            */
-    uint32_t voxels_occupied;   /* voxels holding at least one point                                  */
-    uint32_t voxels_brute;      /* occupied voxels routed to the exhaustive kernel                    */
-    uint32_t work_items;        /* (voxel, <=64-point slice) items processed by the tile kernel       */
-    uint32_t mode_used;         /* TM_MODE_BRUTE or TM_MODE_GRID                                      */
-    float    cell_size;         /* voxel edge actually used                                           */
-    uint32_t grid_dim[3];       /* voxel grid extent                                                  */
+    uint64_t pairs_evaluated;   /* full (point, cylinder) evaluations in reference arithmetic, all kernels   */
+    uint64_t cull_tests;        /* capsule lower-bound tests that decided whether a pair is evaluated        */
+    uint64_t points_grid;       /* points certified by their own voxel's tile                                */
+    uint64_t points_ring;       /* points certified by the search of neighbouring voxel shells               */
+    uint64_t points_brute;      /* points answered by the exhaustive kernel (outliers, brute mode)           */
+    uint64_t index_entries;     /* (voxel, cylinder) entries of the static voxel index                       */
+    uint32_t voxels_occupied;   /* voxels holding at least one point                                         */
+    uint32_t work_items;        /* (voxel, <=64-point slice) items processed by the tile kernel              */
+    uint32_t mode_used;         /* TM_MODE_BRUTE or TM_MODE_GRID                                             */
+    float    cell_size;         /* voxel edge actually used                                                  */
+    float    reach;             /* certified radius D of the tiles                                           */
+    uint32_t grid_dim[3];       /* voxel grid extent                                                         */
 } tm_stats;
 
 int tm_version(void);                                   /* returns TM_ABI_VERSION                     */
@@ -112,8 +114,9 @@ int tm_prepare_cylinders(tm_handle *h,
 /*
  * Install the cylinder table (the cylinder arguments of closest_cylinder_cuda_batch,
  * LabelGenerationCuda.py:20 / Projection.py:19).  The values are used exactly as given
- * (axis_unit / axis_length are NOT recomputed).  Packs two float4 records per cylinder,
- * computes solid-cylinder AABBs and bins them into the uniform voxel grid.
+ * (axis_unit / axis_length are NOT recomputed).  Packs two float4 records per cylinder and
+ * computes capsule AABBs; the static voxel index (per-voxel cylinder tiles) is built on the first
+ * grid-mode call for a given cell size.
  * ids may be NULL (then id == row index).  Synchronises `stream` (it sizes the grid on the host).
  */
 int tm_set_cylinders(tm_handle *h,
@@ -162,12 +165,13 @@ int tm_get_stats(tm_handle *h, tm_stats *out);
 /*
  * Per-phase device timing of tm_label_points (CUDA events recorded on the caller's stream between the
  * phases; off by default).  tm_get_phase_ms synchronises and fills out[0..TM_PHASES):
- *   [0] bin points into voxels   [1] voxel scan / compaction   [2] scatter into voxel order
- *   [3] candidate-tile build     [4] tile evaluate + fused label/offset write
- *   [5] exhaustive kernel (brute mode, or the grid's outliers)   [6] exhaustive finalize   [7] whole call
+ *   [0] bin points into voxels   [1] voxel scan + work items   [2] scatter into voxel order
+ *   [3] tile kernel: cull + dense evaluation + fused record write   [4] ring search of uncertified points
+ *   [5] exhaustive kernel (brute mode, or the grid's outliers)   [6] winner epilogue of pending / brute points
+ *   [7] records -> output arrays   [8] whole call
  * Phases that did not run report 0.
  */
-#define TM_PHASES 8
+#define TM_PHASES 9
 int tm_set_profiling(tm_handle *h, int enabled);
 int tm_get_phase_ms(tm_handle *h, float *out_ms);
 
