@@ -47,52 +47,70 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  The timed region of this path is tens of
+    milliseconds, shorter than nvidia-smi's sampling period, so NVML is polled in-process from a thread every
+    millisecond (same counters as the B200_PROFILING.md nvidia-smi line); nvidia-smi is the fallback."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.thread, self.gpu = [], None, None, gpu_index
+        self.gpu, self.rows, self.thread, self.stop_flag, self.nvml, self.handle = gpu_index, [], None, False, None, None
+        self.smax = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
             return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread = threading.Thread(target=self._poll, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((time.time(), float(clk), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                clk, mx = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            smax = mx
-            if t0 <= ts <= t1 + 0.2:
-                sm.append(clk)
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:                           # timed region shorter than the sampling period: take the nearest samples
-            sm = [float(l.split(",")[1]) for _, l in self.rows[-3:] if l.count(",") >= 8]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.nvml is None:
+            return self._smi_once()
+        inside = [(c, r) for ts, c, r in self.rows if t0 <= ts <= t1]
+        if not inside:                        # region shorter than one poll: nearest samples
+            inside = [(c, r) for _, c, r in sorted(self.rows, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:3]]
+        reasons = sorted(name for name, bit in self.REASONS.items() if any(r & bit for _, r in inside))
+        return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.smax,
+                "reasons": reasons, "samples": len(inside), "source": "NVML polled every 1 ms during the timed region"}
+
+    def _smi_once(self) -> dict:
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout
+            f = [x.strip() for x in out.strip().split(",")]
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                    "reasons": [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi, one sample right after the timed region"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
 def build_workload(seed_points: int):
@@ -253,7 +271,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     if world > 1:
         dist.barrier()

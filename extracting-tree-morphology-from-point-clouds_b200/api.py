@@ -222,6 +222,12 @@ class Engine:
         self._check(self._lib.tm_get_phase_ms(self._h, buf))
         return dict(zip(B.PHASE_NAMES, (float(v) for v in buf)))
 
+    def selftest_arithmetic(self, n: int = 1 << 24, seed: int = 1) -> int:
+        """Mismatches of the kernels' division / square-root sequences against IEEE __fdiv_rn / __fsqrt_rn."""
+        bad = ctypes.c_uint64()
+        self._check(self._lib.tm_selftest_arithmetic(self._h, int(n), int(seed), ctypes.byref(bad)))
+        return int(bad.value)
+
     def fp32_peak(self) -> float:
         """Measured FP32 lane-operations per second of this GPU (FFMA / FADD+FMUL chains)."""
         v = ctypes.c_double()

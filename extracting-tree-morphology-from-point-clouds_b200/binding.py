@@ -58,6 +58,7 @@ SIGNATURES = {
     "tm_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "tm_get_phase_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f32)]),
     "tm_measure_fp32_peak": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double)]),
+    "tm_selftest_arithmetic": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]),
 }
 
 _lib = None

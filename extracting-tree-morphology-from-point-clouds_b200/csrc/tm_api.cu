@@ -139,6 +139,55 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float *out, int iters, 
     if (s == 123.456f) out[0] = s;   // never true in practice; keeps the chains alive
 }
 
+// ------------------------------------------------------------------------------------------------
+// arithmetic self-test: div3 / sqrt_rn against the compiler's IEEE routines
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// operand classes: 0 = the kernel's regime (components of a vector over its norm), 1 = random bit patterns
+// (every exponent, denormals, NaN, inf), 2 = edge values
+__global__ void selftest_kernel(uint64_t n, uint32_t seed, unsigned long long *__restrict__ bad) {
+    unsigned long long local = 0;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t a = mix32(static_cast<uint32_t>(i) * 4u + seed), b = mix32(a + 1u), c = mix32(b + 2u), d = mix32(c + 3u);
+        float x, y, z, rho;
+        const uint32_t cls = static_cast<uint32_t>(i % 3u);
+        // numerators stay in div3's documented domain: |numerator| <= ~|rho| and either 0 or >= 2^-103
+        const float f1 = __uint_as_float((b & 0x007fffffu) | 0x3f800000u) - 1.5f;     // [-0.5, 0.5)
+        const float f2 = (__uint_as_float((c & 0x007fffffu) | 0x3f800000u) - 1.5f) * 2.f;
+        const float f3 = __uint_as_float((d & 0x007fffffu) | 0x3f800000u) - 1.f;      // [0, 1)
+        if (cls == 0) {                 // a vector over its own norm, scales 2^-30 .. 2^29
+            const float sc = __uint_as_float(((a >> 9) % 60u + 97u) << 23);
+            x = f1 * sc; y = f2 * sc; z = f3 * sc;
+            rho = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        } else if (cls == 1) {          // any denominator bit pattern: every exponent, denormals, NaN, inf, negative
+            rho = __uint_as_float(a);
+            x = __fmul_rn(rho, f1); y = __fmul_rn(rho, f2); z = __fmul_rn(rho, f3);
+        } else {                        // edge denominators
+            const float edge[8] = {0.f, -0.f, 1e-8f, 1.17549435e-38f, 1e-45f, __int_as_float(0x7f800000), 3.4e38f, 1.f};
+            rho = edge[a & 7u];
+            x = __fmul_rn(rho, f1); y = (a & 8u) ? rho : 0.f; z = (a & 16u) ? __fmul_rn(rho, f3) : -rho;
+        }
+        if (fabsf(x) < 9.86e-32f) x = 0.f;
+        if (fabsf(y) < 9.86e-32f) y = 0.f;
+        if (fabsf(z) < 9.86e-32f) z = 0.f;
+        float qx, qy, qz;
+        div3(x, y, z, rho, qx, qy, qz);
+        const float ex = __fdiv_rn(x, rho), ey = __fdiv_rn(y, rho), ez = __fdiv_rn(z, rho);
+        auto same = [](float p, float q) { return __float_as_uint(p) == __float_as_uint(q) || (p != p && q != q); };
+        if (!same(qx, ex) || !same(qy, ey) || !same(qz, ez)) ++local;
+        // square root: arbitrary bit patterns, IEEE for every operand
+        const float sq_in[6] = {fabsf(x), rho, __fmul_rn(x, x), __uint_as_float(b), __uint_as_float(c & 0x7fffffffu), -fabsf(y)};
+        for (int k = 0; k < 6; ++k)
+            if (!same(sqrt_rn(sq_in[k]), __fsqrt_rn(sq_in[k]))) ++local;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 }  // namespace tmn
 
 using namespace tmn;
@@ -496,6 +545,20 @@ int tm_get_phase_ms(tm_handle *h, float *out_ms) {
         TM_CUDA(h, cudaEventElapsedTime(&out_ms[p], h->phase_ev[p], h->phase_ev[q]));
     }
     TM_CUDA(h, cudaEventElapsedTime(&out_ms[8], h->phase_ev[0], h->phase_ev[9]));
+    return TM_OK;
+}
+
+int tm_selftest_arithmetic(tm_handle *h, uint64_t n, uint32_t seed, uint64_t *mismatches) {
+    if (!h || !mismatches) return TM_ERR_INVALID;
+    TM_CUDA(h, cudaSetDevice(h->device));
+    TM_CUDA(h, h->scratch_f.ensure(256));
+    unsigned long long *bad = h->scratch_f.as<unsigned long long>();
+    TM_CUDA(h, cudaMemset(bad, 0, sizeof(unsigned long long)));
+    selftest_kernel<<<h->sm_count * 8, 256>>>(n, seed, bad);
+    TM_CUDA(h, cudaGetLastError());
+    unsigned long long host = 0;
+    TM_CUDA(h, cudaMemcpy(&host, bad, sizeof(host), cudaMemcpyDeviceToHost));
+    *mismatches = host;
     return TM_OK;
 }
 

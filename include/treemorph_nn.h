@@ -182,6 +182,13 @@ int tm_get_phase_ms(tm_handle *h, float *out_ms);
  */
 int tm_measure_fp32_peak(tm_handle *h, double *lane_ops_per_second);
 
+/*
+ * Self-test of the division / square-root sequences of the pair evaluation (csrc/tm_eval.cuh: div3, sqrt_rn)
+ * against the compiler's IEEE-rounded __fdiv_rn / __fsqrt_rn on n pseudo-random operand sets (the kernel's
+ * regime, random bit patterns, edge values).  *mismatches must come back 0.  Synchronous.
+ */
+int tm_selftest_arithmetic(tm_handle *h, uint64_t n, uint32_t seed, uint64_t *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

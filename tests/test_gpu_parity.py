@@ -204,6 +204,82 @@ def test_third_call_site_regime_small_m(eng):
     assert ((rdist < 0.1) == (ora["dist"] < 0.1)).all()
 
 
+def test_arithmetic_selftest(eng):
+    """div3 / sqrt_rn of the pair evaluation are bit-identical to the compiler's IEEE __fdiv_rn / __fsqrt_rn."""
+    assert eng.selftest_arithmetic(1 << 25, seed=7) == 0
+    assert eng.selftest_arithmetic(1 << 22, seed=12345) == 0
+
+
+def _append_cylinders(case, rows):
+    """rows: (start xyz, unit xyz, length, radius) appended to the case's fp32 kernel inputs."""
+    rows = np.asarray(rows, dtype=np.float32)
+    out = dict(case)
+    out["start"] = np.concatenate([case["start"], rows[:, 0:3]])
+    out["unit"] = np.concatenate([case["unit"], rows[:, 3:6]])
+    out["length"] = np.concatenate([case["length"], rows[:, 6:7]])
+    out["radius"] = np.concatenate([case["radius"], rows[:, 7]])
+    out["ids"] = np.concatenate([case["ids"], np.arange(len(rows), dtype=np.int32) + 900000])
+    return out
+
+
+@pytest.mark.parametrize("vn", ["A", "B"])
+def test_axis_parallel_cylinders_far_away(eng, vn):
+    """Variant A gives NaN (which wins the argmin) to every point exactly on the axis LINE of an axis-parallel
+    cylinder, however far away; pruning must not lose those.  Variant B has no NaN; it must match as well."""
+    case = _append_cylinders(make_case(3000, 30_000, seed=71, variant=vn),
+                             [[7.0, -3.0, 40.0, 0, 0, 1, 1.0, 0.1],        # vertical, 40 m above the tree
+                              [-25.0, 0.5, 2.0, 1, 0, 0, 0.7, 0.05],       # along x, 25 m to the side
+                              [0.25, 30.0, 1.5, 0, -1, 0, 0.5, 0.02],      # along -y
+                              [7.0, -3.0, 44.0, 0, 0, 1, 1.0, 0.1]])       # same line as the first: lowest index wins
+    pts = case["points"].copy()
+    pts[:200, 0], pts[:200, 1] = 7.0, -3.0                                  # on the line of rows M and M+3
+    pts[200:400, 1], pts[200:400, 2] = 0.5, 2.0                             # on the line of row M+1
+    pts[400:500, 0], pts[400:500, 2] = 0.25, 1.5                            # on the line of row M+2
+    ora = oracle_label(case, pts)
+    if vn == "A":
+        assert np.isnan(ora["dist"][:500]).all() and (ora["index"][:200] == 3000).all()
+    _install(eng, case)
+    with np.errstate(all="ignore"):
+        for mode in ("grid", "brute"):
+            got = _label(eng, case, pts, mode)
+            assert_parity(got, ora, f"axis-parallel/{vn}/{mode}", require_bitwise=True)
+
+
+@pytest.mark.parametrize("vn", ["A", "B"])
+def test_long_special_and_remote_cylinders(eng, vn):
+    """Cylinders the voxel index cannot list the usual way: one spanning > 32k voxels (long list), one with a
+    non-unit axis and one with NaN entries (special list: evaluated for every point), plus points that sit in
+    voxels with empty tiles (ring search) and far outside the grid (exhaustive kernel with the cull)."""
+    base = make_case(2500, 40_000, seed=81, variant=vn)
+    d = np.array([1.0, 1.0, 1.0], np.float32) / np.sqrt(np.float32(3))
+    rows = [[-6.0, -6.0, 0.0, d[0], d[1], d[2], 20.8, 0.05],                # 20.8 m diagonal: long list
+            [1.0, 1.0, 3.0, 0.5, 0.0, 0.0, 1.0, 0.1],                       # |u| = 0.5: special
+            [-2.0, 2.0, 2.0, 0.0, 0.6, 0.8, 0.4, 0.03]]
+    case = _append_cylinders(base, rows)
+    rng = np.random.default_rng(82)
+    t = rng.uniform(0, 20.8, 4000).astype(np.float32)
+    along = np.array([-6.0, -6.0, 0.0], np.float32) + t[:, None] * d + rng.normal(0, 0.05, (4000, 3)).astype(np.float32)
+    remote = (rng.uniform(-1, 1, (3000, 3)) * [9, 9, 3] + [0, 0, 14]).astype(np.float32)      # inside the grid, empty tiles
+    far = (rng.normal(0, 60, (500, 3))).astype(np.float32)                                      # mostly outside the grid
+    pts = np.concatenate([case["points"], along, remote, far])
+    ora = oracle_label(case, pts)
+    _install(eng, case)
+    st = None
+    for mode in ("grid", "brute"):
+        got = _label(eng, case, pts, mode)
+        st = st or eng.stats()
+        assert_parity(got, ora, f"long+special/{vn}/{mode}", require_bitwise=True)
+    # a NaN row in the table: variant A answers every point with it, variant B too where NaN propagates
+    case2 = _append_cylinders(base, [[np.nan, 0.0, 0.0, 0, 0, 1, 1.0, 0.1]])
+    ora2 = oracle_label(case2, pts[:20_000])
+    _install(eng, case2)
+    with np.errstate(all="ignore"):
+        got2 = _label(eng, case2, pts[:20_000], "grid")
+        assert_parity(got2, ora2, f"nan-row/{vn}", require_bitwise=True)
+    assert st["mode_used"] == 2 and st["points_ring"] > 0 and st["points_brute"] > 0
+    assert st["points_grid"] + st["points_ring"] + st["points_brute"] == len(pts)
+
+
 # ---- full-size properties ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,m", [(1_000_000, 10_000), (10_000_000, 50_000)])
