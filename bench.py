@@ -375,7 +375,7 @@ def main():
                "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {oracle.max_threads()} threads "
                          f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
 
-    launches_per_step = {"grid": 9, "auto": 9, "brute": 2}[args.mode]
+    launches_per_step = {"grid": 10, "auto": 10, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, ring, exhaustive, finalize, unpack
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -230,7 +230,7 @@ int tm_destroy(tm_handle *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
-                          &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
+                          &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
                           &h->pend_idx, &h->brute_slots, &h->rec, &h->dstats, &h->scratch_f};
     for (auto *b : bufs) b->release();
@@ -342,7 +342,7 @@ int tm_label_points(tm_handle *h, const float *pts, int64_t n, int64_t row_strid
     for (bool &b : h->phase_hit) b = false;
     mark(h, 0, a.stream);
     rc = label_dispatch(h, a);
-    mark(h, 9, a.stream);
+    mark(h, TM_PHASES - 1, a.stream);
     return rc;
 }
 
@@ -508,7 +508,8 @@ int tm_get_stats(tm_handle *h, tm_stats *out) {
         TM_CUDA(h, cudaMemcpy(&d, h->dstats.p, sizeof(d), cudaMemcpyDeviceToHost));
         s.pairs_evaluated += d.pairs_grid + d.pairs_ring;
         s.cull_tests += d.cull_tests;
-        s.points_grid += static_cast<uint64_t>(h->last_n) - d.pending;
+        s.points_grid += static_cast<uint64_t>(h->last_n) - d.pending - d.far_certified;
+        s.points_far += d.far_certified;
         s.points_ring += d.pending - d.n_brute;
         s.points_brute += d.n_brute;
         s.index_entries = h->index_entries;
@@ -516,6 +517,7 @@ int tm_get_stats(tm_handle *h, tm_stats *out) {
         s.work_items = d.work_items;
         s.cell_size = h->grid.h;
         s.reach = h->reach;
+        s.near_reach = h->near;
         s.grid_dim[0] = static_cast<uint32_t>(h->grid.nx);
         s.grid_dim[1] = static_cast<uint32_t>(h->grid.ny);
         s.grid_dim[2] = static_cast<uint32_t>(h->grid.nz);
@@ -533,18 +535,19 @@ int tm_set_profiling(tm_handle *h, int enabled) {
 int tm_get_phase_ms(tm_handle *h, float *out_ms) {
     if (!h || !out_ms) return TM_ERR_INVALID;
     for (int i = 0; i < TM_PHASES; ++i) out_ms[i] = 0.f;
-    if (!h->profiling || !h->phase_hit[0] || !h->phase_hit[9]) return TM_OK;
+    constexpr int END = TM_PHASES - 1;
+    if (!h->profiling || !h->phase_hit[0] || !h->phase_hit[END]) return TM_OK;
     TM_CUDA(h, cudaSetDevice(h->device));
-    TM_CUDA(h, cudaEventSynchronize(h->phase_ev[9]));
-    // phase p spans mark p -> the next mark that was recorded (mark 9 = end of the call)
-    for (int p = 0; p < 8; ++p) {
+    TM_CUDA(h, cudaEventSynchronize(h->phase_ev[END]));
+    // phase p spans mark p -> the next mark that was recorded (mark END = end of the call)
+    for (int p = 0; p < END; ++p) {
         if (!h->phase_hit[p]) continue;
         int q = p + 1;
-        while (q < 9 && !h->phase_hit[q]) ++q;
+        while (q < END && !h->phase_hit[q]) ++q;
         if (p == 0 && !h->phase_hit[1]) continue;          // brute mode has no binning phase
         TM_CUDA(h, cudaEventElapsedTime(&out_ms[p], h->phase_ev[p], h->phase_ev[q]));
     }
-    TM_CUDA(h, cudaEventElapsedTime(&out_ms[8], h->phase_ev[0], h->phase_ev[9]));
+    TM_CUDA(h, cudaEventElapsedTime(&out_ms[END], h->phase_ev[0], h->phase_ev[END]));
     return TM_OK;
 }
 

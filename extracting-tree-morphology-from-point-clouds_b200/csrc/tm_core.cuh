@@ -55,7 +55,8 @@ struct DevStats {
     unsigned int work_items;
     unsigned int pending;            // points the voxel-tile kernel could not certify (slots of pend_idx / keys)
     unsigned int n_brute;            // of those, points that need the exhaustive kernel (slots of brute_slots)
-    unsigned int pad[2];
+    unsigned int far_certified;      // points certified by the far part of their own tile (inside the tile kernel)
+    unsigned int pad[1];
 };
 
 }  // namespace tmn
@@ -76,12 +77,16 @@ struct tm_handle {
     // ---- static voxel index of the cylinders (per table and cell size) ----
     bool have_grid = false;
     float grid_cell = 0.f;          // cell size the index was requested with
-    float reach = 0.f;              // certified radius D: list(V) holds every cylinder within D of voxel V
+    float reach = 0.f;              // D_max: tile(V) holds every cylinder whose capsule comes within D_max of voxel V
+    float near = 0.f;               // D_near: the leading `near` entries of a tile are those within D_near of the voxel
     float maxabs = 0.f;             // largest |coordinate| of the grid (scales the rounding slack)
     tmn::GridDesc grid{};
     tmn::DevBuf cyl_cell_start;      // uint32[ncell_codes + 1]: first pool entry of each voxel's tile (multiple of 4)
     tmn::DevBuf cyl_cell_cnt;        // uint32[ncell_codes]: tile length
-    tmn::DevBuf tileA, tileB, tileI; // tile pool: packed records + cylinder row of every (voxel, cylinder) entry
+    tmn::DevBuf cyl_cell_near;       // uint32[ncell_codes]: length of the tile's near part (lower bound <= D_near)
+    tmn::DevBuf tileA, tileB, tileI; // tile pool: packed records + cylinder row of every (voxel, cylinder) entry,
+    tmn::DevBuf tileLB;              //            sorted per voxel by tileLB = lower bound of dist(voxel box, capsule)
+    tmn::DevBuf tile_keys;           // u64 per entry, build-time only: (bits(lower bound) << 32) | cylinder row
     tmn::DevBuf long_list;           // int32[]: cylinders whose dilated AABB spans too many voxels
     tmn::DevBuf special;             // int32[]: non-finite / non-unit cylinders, evaluated for every point
     tmn::DevBuf aligned;             // int32[]: axis-parallel cylinders (variant A: NaN for points on their axis LINE)
@@ -110,8 +115,8 @@ struct tm_handle {
 
     // ---- optional phase timing ----
     bool profiling = false;
-    cudaEvent_t phase_ev[10] = {nullptr};
-    bool phase_hit[10] = {false};
+    cudaEvent_t phase_ev[TM_PHASES + 1] = {nullptr};
+    bool phase_hit[TM_PHASES + 1] = {false};
 
     tm_stats stats{};
     int64_t last_n = 0;             // point count of the most recent labelling call (for tm_get_stats)
@@ -147,7 +152,7 @@ inline bool debug_sync() {
     return on;
 }
 
-// phase marks: event i is recorded when phase i-1 ends / phase i begins (0 = call start, 9 = call end)
+// phase marks: event i is recorded when phase i-1 ends / phase i begins (0 = call start, TM_PHASES = call end)
 inline void mark(tm_handle *h, int i, cudaStream_t st) {
     if (!h->profiling) return;
     if (!h->phase_ev[i]) cudaEventCreate(&h->phase_ev[i]);

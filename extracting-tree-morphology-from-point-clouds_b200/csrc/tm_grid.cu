@@ -1,30 +1,32 @@
 // Voxel-grid path: exact nearest-cylinder search with spatial pruning.
 //
 //   per table (tm_set_cylinders + first use of a cell size):
-//     cylinders --> capsule AABBs --> every voxel V within D of a cylinder gets that cylinder in its TILE:
-//     tile(V) = { c : dist(capsule(c), box(V)) <= D }, packed contiguously (float4 A | float4 B | row index)
+//     every voxel V gets a TILE: the cylinders whose capsule comes within D_max of box(V), sorted by
+//     lb(V, c) = a lower bound of dist(box(V), capsule(c)), packed contiguously (float4 A | float4 B | row | lb).
+//     The leading `near(V)` entries are those with lb <= D_near.
 //   per call:
-//     points --bin--> counting sort by voxel id (brick-Morton order) --> contiguous per-voxel runs
-//     evaluate:  one warp per (voxel, <= 64 points) work item.  The voxel's tile is staged into shared memory with
-//                bulk async copies (double buffered, next item's tile prefetched).  For every tile entry each lane
-//                runs a 17-instruction capsule lower-bound test for its (up to) two points against the point's
-//                incumbent; surviving (point, entry) pairs are compacted into a per-warp queue (ballot + popc) and
-//                evaluated 32 at a time with the reference arithmetic, so the expensive evaluation always runs with
-//                full lanes.  Winners are merged with a 64-bit (distance, index) atomicMin in shared memory, which
-//                is torch.argmin's comparator.
-//                A point whose best distance is <= D is CERTIFIED: every cylinder that could beat or tie it lies
-//                within D of the point, hence within D of its voxel, hence in the tile.  Its label + offset are
-//                written by the fused winner-only epilogue as one 32-byte record at the original row.
-//     ring:      the few points that are not certified (noise tail, empty tiles) search the tiles of the
-//                surrounding voxel shells, one warp per point, until the searched radius covers their incumbent.
+//     points --count/scan/scatter--> counting sort by voxel id (brick-Morton order) --> contiguous per-voxel runs
+//     evaluate:  one warp per (voxel, <= 64 points) work item.  The NEAR part of the voxel's tile is staged into shared
+//                memory with bulk async copies (double buffered, next item's tile prefetched).  For every tile entry
+//                each lane runs a 17-instruction capsule lower-bound test for its (up to) two points against the
+//                point's incumbent; surviving (point, entry) pairs are compacted into a per-warp queue (ballot +
+//                popc) and evaluated 32 at a time with the reference arithmetic, so the expensive evaluation always
+//                runs with full lanes.  Winners are merged with a 64-bit (distance, index) atomicMin in shared
+//                memory, which is torch.argmin's comparator.
+//                A point whose best distance is <= D_near is CERTIFIED: every cylinder that could beat or tie it has
+//                lb <= D_near for the point's voxel, i.e. sits in the near part.  Its label + offset are written by
+//                the fused winner-only epilogue as one 32-byte record at the original row.
+//                The few points that are not certified (noise tail) then walk the FAR part of the tile, lanes across
+//                entries in ascending lb order, and stop at the first entry whose lb exceeds their incumbent.
+//     ring:      points still uncertified at D_max search the tiles of the surrounding voxel shells, one CTA per point.
 //     brute:     points outside the grid / not certified within RING_MAX shells: exhaustive search with the same cull.
 //     unpack:    records --> the caller's output arrays, coalesced.
 //
-// Exactness: dist_ref(p,c) >= dist(p, capsule(c)); the cull and the certification only ever
-// discard cylinders whose capsule is farther than the incumbent (plus a rounding allowance), so the argmin and
-// its lowest-index tie-break are those of the exhaustive search.  Cylinders that cannot be bounded (non-finite,
-// non-unit axis) are evaluated for every point; axis-parallel cylinders get the exact on-axis-line test in
-// variant A (NaN wins the argmin at any distance).
+// Exactness: dist_ref(p,c) >= dist(p, capsule(c)) >= lb(V,c) for p in V; the cull, the lb order and
+// the certification only ever discard cylinders whose capsule is farther than the incumbent (plus a rounding
+// allowance), so the argmin and its lowest-index tie-break are those of the exhaustive search.  Cylinders that cannot
+// be bounded (non-finite, non-unit axis) are evaluated for every point; axis-parallel cylinders get the exact
+// on-axis-line test in variant A (NaN wins the argmin at any distance).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -43,7 +45,8 @@ struct GridDev {
     int nx, ny, nz;        // voxels
     int bnx, bny, bnz;     // bricks
     float slack;           // fp32 rounding allowance of the reference pipeline at this coordinate scale
-    float reach;           // D: certified radius of the tiles
+    float reach;           // D_max: radius covered by a whole tile
+    float near;            // D_near: radius covered by the near part of a tile
 };
 
 __host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {      // 3 bits -> every third bit
@@ -55,13 +58,14 @@ __host__ __device__ __forceinline__ uint32_t voxel_code(const GridDev &g, int x,
     return (brick << 9) | spread3(x & 7) | (spread3(y & 7) << 1) | (spread3(z & 7) << 2);
 }
 
-static GridDev to_dev(const GridDesc &d, float slack, float reach) {
+static GridDev to_dev(const GridDesc &d, float slack, float reach, float near) {
     GridDev g;
     g.ox = d.ox; g.oy = d.oy; g.oz = d.oz; g.h = d.h; g.inv_h = d.inv_h;
     g.nx = d.nx; g.ny = d.ny; g.nz = d.nz;
     g.bnx = (d.nx + 7) / 8; g.bny = (d.ny + 7) / 8; g.bnz = (d.nz + 7) / 8;
     g.slack = slack;
     g.reach = reach;
+    g.near = near;
     return g;
 }
 
@@ -76,13 +80,41 @@ __device__ __forceinline__ int cell_coord(float p, float o, float inv_h, int n) 
 // ------------------------------------------------------------------------------------------------
 constexpr int LONG_CELLS = 1 << 15;   // dilated AABBs spanning more voxels than this go to the "long" list
 
-// One warp per cylinder.  pass 0 counts, pass 1 fills: voxel V receives cylinder c when the capsule of c comes
-// within D + (half diagonal of V) of V's centre, a superset of { dist(capsule, box(V)) <= D }.
+// dist(axis segment of the cylinder, box [lo, lo + h]^3), from below.  f(t) = dist^2(start + t * unit, box) is convex
+// in t, so a golden-section search keeps the minimiser bracketed; the distance is 1-Lipschitz in t (|unit| = 1), hence
+// min over the final bracket >= sqrt(best sample) - bracket width.
+__device__ __forceinline__ float seg_box_dist2(const float4 A, const float4 B, float lx, float ly, float lz, float h, float t) {
+    const float x = fmaf(t, B.x, A.x), y = fmaf(t, B.y, A.y), z = fmaf(t, B.z, A.z);
+    const float gx = fmaxf(fmaxf(lx - x, x - (lx + h)), 0.f);
+    const float gy = fmaxf(fmaxf(ly - y, y - (ly + h)), 0.f);
+    const float gz = fmaxf(fmaxf(lz - z, z - (lz + h)), 0.f);
+    return fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+}
+
+__device__ __forceinline__ float seg_box_lower_bound(const float4 A, const float4 B, float lx, float ly, float lz, float h) {
+    constexpr float INVPHI = 0.61803398875f;
+    float lo = 0.f, hi = A.w;
+    float c = hi - (hi - lo) * INVPHI, d = lo + (hi - lo) * INVPHI;
+    float fc = seg_box_dist2(A, B, lx, ly, lz, h, c), fd = seg_box_dist2(A, B, lx, ly, lz, h, d);
+    float best = fminf(fminf(fc, fd), fminf(seg_box_dist2(A, B, lx, ly, lz, h, lo), seg_box_dist2(A, B, lx, ly, lz, h, hi)));
+#pragma unroll 1
+    for (int it = 0; it < 26; ++it) {
+        if (fc < fd) { hi = d; d = c; fd = fc; c = hi - (hi - lo) * INVPHI; fc = seg_box_dist2(A, B, lx, ly, lz, h, c); best = fminf(best, fc); }
+        else         { lo = c; c = d; fc = fd; d = lo + (hi - lo) * INVPHI; fd = seg_box_dist2(A, B, lx, ly, lz, h, d); best = fminf(best, fd); }
+    }
+    return sqrtf(best) - (hi - lo);
+}
+
+// One warp per cylinder.  pass 0 counts, pass 1 fills: voxel V receives cylinder c when
+//   lb_raw(V, c) = dist(box(V), axis segment) - |r|  <=  D_max + slack,
+// and the entry carries lb = max(0, lb_raw - slack - margin), a lower bound of the reference distance between any
+// point binned into V and c (slack absorbs the fp32 rounding of the binning, of this arithmetic and of the
+// reference pipeline).  Entries are written as sortable keys (bits(lb) << 32 | c); tile_sort_kernel orders them.
 __global__ void __launch_bounds__(256)
 cyl_register_kernel(const float4 *__restrict__ recA, const float4 *__restrict__ recB, const float4 *__restrict__ boxlo,
                     const float4 *__restrict__ boxhi, int m, GridDev g, int pass, uint32_t *__restrict__ cell_counter,
-                    const uint32_t *__restrict__ cell_start, float4 *__restrict__ tileA, float4 *__restrict__ tileB,
-                    int32_t *__restrict__ tileI, int32_t *__restrict__ long_list, unsigned int *__restrict__ n_long) {
+                    const uint32_t *__restrict__ cell_start, unsigned long long *__restrict__ tile_keys,
+                    int32_t *__restrict__ long_list, unsigned int *__restrict__ n_long) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (c >= m) return;
@@ -99,22 +131,89 @@ cyl_register_kernel(const float4 *__restrict__ recA, const float4 *__restrict__ 
         return;
     }
     const float4 A = recA[c], B = recB[c];
-    const float lim = grow + 0.8660254f * g.h * 1.0001f + fabsf(B.w);
+    const float ar = fabsf(B.w);
+    const float lim = grow + 0.8660254f * g.h * 1.0001f + ar;      // cheap reject: capsule vs the voxel's circumsphere
     const float lim2 = lim * lim;
     for (int idx = lane; idx < static_cast<int>(cells); idx += 32) {
         const int x = x0 + idx % sx, y = y0 + (idx / sx) % sy, z = z0 + idx / (sx * sy);
-        const float vx = g.ox + (x + 0.5f) * g.h - A.x, vy = g.oy + (y + 0.5f) * g.h - A.y, vz = g.oz + (z + 0.5f) * g.h - A.z;
+        const float lx = g.ox + x * g.h, ly = g.oy + y * g.h, lz = g.oz + z * g.h;
+        const float vx = lx + 0.5f * g.h - A.x, vy = ly + 0.5f * g.h - A.y, vz = lz + 0.5f * g.h - A.z;
         const float t = fminf(fmaxf(vx * B.x + vy * B.y + vz * B.z, 0.f), A.w);
         const float wx = vx - t * B.x, wy = vy - t * B.y, wz = vz - t * B.z;
         if (wx * wx + wy * wy + wz * wz > lim2) continue;
+        const float lb_raw = seg_box_lower_bound(A, B, lx, ly, lz, g.h) - ar;
+        if (lb_raw > grow) continue;
         const uint32_t code = voxel_code(g, x, y, z);
         const uint32_t s = atomicAdd(&cell_counter[code], 1u);
         if (pass == 1) {
-            const uint32_t pos = cell_start[code] + s;
-            tileA[pos] = A;
-            tileB[pos] = B;
-            tileI[pos] = c;
+            const float lb = fmaxf(lb_raw - 2.f * g.slack, 0.f);
+            tile_keys[cell_start[code] + s] = (static_cast<unsigned long long>(__float_as_uint(lb)) << 32) | static_cast<uint32_t>(c);
         }
+    }
+}
+
+// One warp per voxel: order the tile's keys by (lb, cylinder row) and expand them into the pool arrays.
+// Tiles longer than SORT_MAX keep their arbitrary order with lb = 0 (always a valid lower bound): everything is "near".
+constexpr int SORT_MAX = 1024;
+constexpr int SORT_WARPS = 8;
+
+__global__ void __launch_bounds__(SORT_WARPS * 32)
+tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_cnt, uint32_t ncodes,
+                 const unsigned long long *__restrict__ tile_keys, const float4 *__restrict__ recA,
+                 const float4 *__restrict__ recB, float near_reach, float4 *__restrict__ tileA, float4 *__restrict__ tileB,
+                 int32_t *__restrict__ tileI, float *__restrict__ tileLB, uint32_t *__restrict__ cell_near) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(sort_smem) + static_cast<size_t>(warp) * SORT_MAX;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t code = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; code < ncodes; code += nwarps) {
+        const uint32_t n = cell_cnt[code];
+        if (n == 0) { if (lane == 0) cell_near[code] = 0; continue; }
+        const uint32_t off = cell_start[code];
+        uint32_t near = 0;
+        if (n <= SORT_MAX) {
+            uint32_t P = 32;
+            while (P < n) P <<= 1;
+            for (uint32_t i = lane; i < P; i += 32) buf[i] = i < n ? tile_keys[off + i] : KEY_NONE;
+            __syncwarp();
+            for (uint32_t k = 2; k <= P; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = lane; i < P; i += 32) {
+                        const uint32_t ixj = i ^ j;
+                        if (ixj > i) {
+                            const unsigned long long a = buf[i], b = buf[ixj];
+                            const bool asc = (i & k) == 0;
+                            if ((a > b) == asc) { buf[i] = b; buf[ixj] = a; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (uint32_t i = lane; i < n; i += 32) {
+                const unsigned long long key = buf[i];
+                const uint32_t c = static_cast<uint32_t>(key);
+                const float lb = __uint_as_float(static_cast<uint32_t>(key >> 32));
+                tileA[off + i] = recA[c];
+                tileB[off + i] = recB[c];
+                tileI[off + i] = static_cast<int32_t>(c);
+                tileLB[off + i] = lb;
+                near += lb <= near_reach ? 1u : 0u;
+            }
+            __syncwarp();
+        } else {
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t c = static_cast<uint32_t>(tile_keys[off + i]);
+                tileA[off + i] = recA[c];
+                tileB[off + i] = recB[c];
+                tileI[off + i] = static_cast<int32_t>(c);
+                tileLB[off + i] = 0.f;
+            }
+            near = lane == 0 ? n : 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) near += __shfl_xor_sync(0xffffffffu, near, o);
+        if (n - near > 0xFFFFFFu) near = n;          // the far length must fit the 24 bits of a work item
+        if (lane == 0) cell_near[code] = near;
     }
 }
 
@@ -217,12 +316,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(Tri *__restri
 
 // phase C: final offsets.  mode 0 (tile pool): start[code] only (+ the grand total at start[ncodes]).
 // mode 1 (points): start[code] = first sorted point of the voxel, and the voxel's work items
-// {tile offset, tile length, first point, point count <= 64} are emitted in voxel-id order.
+// {tile offset, near length, first point, point count <= 64 | far length << 8} are emitted in voxel-id order.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *__restrict__ count, uint32_t ncodes,
                                                                   const Tri *__restrict__ block_sums, int mode,
                                                                   uint32_t *__restrict__ start,
                                                                   const uint32_t *__restrict__ tile_start,
                                                                   const uint32_t *__restrict__ tile_cnt,
+                                                                  const uint32_t *__restrict__ tile_near,
                                                                   uint4 *__restrict__ items) {
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     uint32_t cnt[SCAN_ITEMS];
@@ -238,11 +338,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
         if (base + i < ncodes) {
             start[base + i] = run.a;
             if (mode == 1 && cnt[i]) {
-                const uint32_t toff = tile_start[base + i], tcnt = tile_cnt[base + i];
+                const uint32_t toff = tile_start[base + i], tcnt = tile_cnt[base + i], tnear = tile_near[base + i];
+                const uint32_t far = tcnt - tnear;                       // < 2^24 (tile_sort_kernel)
                 const uint32_t n_items = (cnt[i] + PTS_PER_ITEM - 1) / PTS_PER_ITEM;
                 for (uint32_t t = 0; t < n_items; ++t)
-                    items[run.c + t] = make_uint4(toff, tcnt, run.a + t * PTS_PER_ITEM,
-                                                  min(static_cast<uint32_t>(PTS_PER_ITEM), cnt[i] - t * PTS_PER_ITEM));
+                    items[run.c + t] = make_uint4(toff, tnear, run.a + t * PTS_PER_ITEM,
+                                                  min(static_cast<uint32_t>(PTS_PER_ITEM), cnt[i] - t * PTS_PER_ITEM) | (far << 8));
             }
         }
         run = tri_add(run, tri_of_count(cnt[i]));
@@ -251,13 +352,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 }
 
 static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mode, uint32_t *start, const uint32_t *tile_start,
-                    const uint32_t *tile_cnt, uint4 *items, DevStats *st, cudaStream_t stream) {
+                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, DevStats *st, cudaStream_t stream) {
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
     Tri *bs = h->block_sums.as<Tri>();
     scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, ncodes, bs);
     scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);
-    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, ncodes, bs, mode, start, tile_start, tile_cnt, items);
+    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, ncodes, bs, mode, start, tile_start, tile_cnt, tile_near, items);
     TM_CUDA(h, cudaGetLastError());
     return TM_OK;
 }
@@ -322,13 +423,18 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     }
     d.bx = d.by = d.bz = 0;
     h->grid = d;
-    float dfac = 1.0f;                  // D = dfac * h (tuning hook for experiments; 1.0 is the shipped value)
-    if (const char *env = getenv("TM_REACH_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v >= 0.25f && v <= 4.f) dfac = v; }
+    // D_near = nfac * h covers the bulk of a surface-sampled cloud; D_max = dfac * h bounds the far part of the tiles
+    // (tuning hooks for experiments; the defaults are the shipped values)
+    float nfac = 1.0f, dfac = 2.0f;
+    if (const char *env = getenv("TM_NEAR_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v >= 0.1f && v <= 4.f) nfac = v; }
+    if (const char *env = getenv("TM_REACH_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v >= 0.25f && v <= 8.f) dfac = v; }
+    if (dfac < nfac) dfac = nfac;
+    h->near = nfac * hcell;
     h->reach = dfac * hcell;
     float maxabs = 0.f;
     for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, std::max(std::fabs(lo[k]), std::fabs(hi[k])) + margin);
     h->maxabs = maxabs;
-    const GridDev g = to_dev(d, slack_for(maxabs), h->reach);
+    const GridDev g = to_dev(d, slack_for(maxabs), h->reach, h->near);
 
     const int m = static_cast<int>(h->m);
     const uint32_t ncodes = d.ncell_codes;
@@ -336,6 +442,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_CUDA(h, h->cell_start.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->cyl_cell_start.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->cyl_cell_cnt.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
+    TM_CUDA(h, h->cyl_cell_near.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->long_list.ensure(sizeof(int32_t) * static_cast<size_t>(m)));
     TM_CUDA(h, h->dstats.ensure(sizeof(DevStats) + 64));
     uint32_t *counter = h->cell_count.as<uint32_t>();
@@ -345,11 +452,11 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_CUDA(h, cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), stream));
     const int blocks = (m + 7) / 8;                               // 8 warps per block, one warp per cylinder
     cyl_register_kernel<<<blocks, 256, 0, stream>>>(h->recA.as<float4>(), h->recB.as<float4>(), h->boxlo.as<float4>(),
-                                                    h->boxhi.as<float4>(), m, g, 0, counter, nullptr, nullptr, nullptr, nullptr,
+                                                    h->boxhi.as<float4>(), m, g, 0, counter, nullptr, nullptr,
                                                     h->long_list.as<int32_t>(), d_nlong);
-    TM_CUDA(h, cudaGetLastError());
+    TM_KCHECK(h, stream, "cyl_register_kernel (count)");
     align4_kernel<<<(ncodes + 255) / 256, 256, 0, stream>>>(counter, h->cyl_cell_cnt.as<uint32_t>(), rounded, ncodes);
-    int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, stream);
+    int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc != TM_OK) return rc;
     uint32_t total = 0, nlong = 0;
     TM_CUDA(h, cudaMemcpyAsync(&total, h->cyl_cell_start.as<uint32_t>() + ncodes, 4, cudaMemcpyDeviceToHost, stream));
@@ -362,16 +469,28 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_CUDA(h, h->tileA.ensure(sizeof(float4) * pool));
     TM_CUDA(h, h->tileB.ensure(sizeof(float4) * pool));
     TM_CUDA(h, h->tileI.ensure(sizeof(int32_t) * pool));
+    TM_CUDA(h, h->tileLB.ensure(sizeof(float) * pool));
+    TM_CUDA(h, h->tile_keys.ensure(sizeof(unsigned long long) * pool));
     // padding entries are copied by the bulk loads (never read): give them defined contents
     TM_CUDA(h, cudaMemsetAsync(h->tileA.p, 0, sizeof(float4) * pool, stream));
     TM_CUDA(h, cudaMemsetAsync(h->tileB.p, 0, sizeof(float4) * pool, stream));
     TM_CUDA(h, cudaMemsetAsync(h->tileI.p, 0, sizeof(int32_t) * pool, stream));
+    TM_CUDA(h, cudaMemsetAsync(h->tileLB.p, 0, sizeof(float) * pool, stream));
     TM_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(uint32_t) * ncodes, stream));
     cyl_register_kernel<<<blocks, 256, 0, stream>>>(h->recA.as<float4>(), h->recB.as<float4>(), h->boxlo.as<float4>(),
                                                     h->boxhi.as<float4>(), m, g, 1, counter, h->cyl_cell_start.as<uint32_t>(),
-                                                    h->tileA.as<float4>(), h->tileB.as<float4>(), h->tileI.as<int32_t>(),
-                                                    h->long_list.as<int32_t>(), d_nlong);
+                                                    h->tile_keys.as<unsigned long long>(), h->long_list.as<int32_t>(), d_nlong);
     TM_KCHECK(h, stream, "cyl_register_kernel (fill)");
+    const size_t sort_smem = sizeof(unsigned long long) * SORT_MAX * SORT_WARPS;
+    TM_CUDA(h, cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sort_smem)));
+    const int sort_blocks = static_cast<int>(std::min<uint32_t>((ncodes + SORT_WARPS - 1) / SORT_WARPS, static_cast<uint32_t>(h->sm_count) * 3));
+    tile_sort_kernel<<<sort_blocks, SORT_WARPS * 32, sort_smem, stream>>>(
+        h->cyl_cell_start.as<uint32_t>(), h->cyl_cell_cnt.as<uint32_t>(), ncodes, h->tile_keys.as<unsigned long long>(),
+        h->recA.as<float4>(), h->recB.as<float4>(), h->near, h->tileA.as<float4>(), h->tileB.as<float4>(),
+        h->tileI.as<int32_t>(), h->tileLB.as<float>(), h->cyl_cell_near.as<uint32_t>());
+    TM_KCHECK(h, stream, "tile_sort_kernel");
+    TM_CUDA(h, cudaStreamSynchronize(stream));
+    h->tile_keys.release();                 // build-time only
     h->have_grid = true;
     return TM_OK;
 }
@@ -382,24 +501,27 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
 constexpr uint32_t NO_CELL = 0xFFFFFFFFu;
 constexpr int32_t OUTSIDE_BIT = static_cast<int32_t>(0x80000000u);
 
+// pass 1: voxel occupancy.  The atomics return nothing (RED): no per-point state is kept between the passes, the
+// scatter pass recomputes the voxel id from the coordinates (cheaper than 8 bytes of HBM traffic per point each way).
+__device__ __forceinline__ uint32_t point_code(const GridDev &g, float x, float y, float z) {
+    const float fx = (x - g.ox) * g.inv_h, fy = (y - g.oy) * g.inv_h, fz = (z - g.oz) * g.inv_h;
+    // NaN / Inf fail these comparisons and become outliers
+    const bool inside = fx >= 0.f && fx < static_cast<float>(g.nx) && fy >= 0.f && fy < static_cast<float>(g.ny) &&
+                        fz >= 0.f && fz < static_cast<float>(g.nz);
+    return inside ? voxel_code(g, static_cast<int>(fx), static_cast<int>(fy), static_cast<int>(fz)) : NO_CELL;
+}
+
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
-                                                        uint32_t *__restrict__ cell_count, uint32_t *__restrict__ pt_cell,
-                                                        uint32_t *__restrict__ pt_rank, int32_t *__restrict__ pend_idx,
+                                                        uint32_t *__restrict__ cell_count, int32_t *__restrict__ pend_idx,
                                                         unsigned long long *__restrict__ pend_keys,
                                                         uint32_t *__restrict__ brute_slots, DevStats *__restrict__ st) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float *p = pts + i * row_stride;
-        const float fx = (p[0] - g.ox) * g.inv_h, fy = (p[1] - g.oy) * g.inv_h, fz = (p[2] - g.oz) * g.inv_h;
-        // NaN / Inf fail these comparisons and become outliers
-        const bool inside = fx >= 0.f && fx < static_cast<float>(g.nx) && fy >= 0.f && fy < static_cast<float>(g.ny) &&
-                            fz >= 0.f && fz < static_cast<float>(g.nz);
-        if (inside) {
-            const uint32_t code = voxel_code(g, static_cast<int>(fx), static_cast<int>(fy), static_cast<int>(fz));
-            pt_cell[i] = code;
-            pt_rank[i] = atomicAdd(&cell_count[code], 1u);
+        const uint32_t code = point_code(g, p[0], p[1], p[2]);
+        if (code != NO_CELL) {
+            atomicAdd(&cell_count[code], 1u);
         } else {
-            pt_cell[i] = NO_CELL;
             const unsigned int s = atomicAdd(&st->pending, 1u);
             pend_idx[s] = static_cast<int32_t>(i) | OUTSIDE_BIT;
             pend_keys[s] = KEY_NONE;
@@ -408,18 +530,19 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
     }
 }
 
-__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride,
-                                                          const uint32_t *__restrict__ pt_cell,
-                                                          const uint32_t *__restrict__ pt_rank,
+// pass 2: each point takes the next free slot of its voxel's run (the counter runs back down to zero)
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
+                                                          uint32_t *__restrict__ cell_count,
                                                           const uint32_t *__restrict__ cell_start,
                                                           float4 *__restrict__ sorted) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const uint32_t code = pt_cell[i];
-        if (code == NO_CELL) continue;
         const float *p = pts + i * row_stride;
-        const uint32_t pos = cell_start[code] + pt_rank[i];
-        sorted[pos] = make_float4(p[0], p[1], p[2], __int_as_float(static_cast<int>(i)));
+        const float x = p[0], y = p[1], z = p[2];
+        const uint32_t code = point_code(g, x, y, z);
+        if (code == NO_CELL) continue;
+        const uint32_t pos = cell_start[code] + atomicSub(&cell_count[code], 1u) - 1u;
+        sorted[pos] = make_float4(x, y, z, __int_as_float(static_cast<int>(i)));
     }
 }
 
@@ -449,7 +572,8 @@ struct EvalArgs {
     const int32_t *ids;
     const int32_t *special, *aligned, *long_list;
     uint32_t n_special, n_aligned, n_long;
-    float atol, eps, slack, reach;
+    const float *tileLB;
+    float atol, eps, slack, near, reach;
     int move_to_mantle;
     float4 *rec;
     int32_t *pend_idx;
@@ -496,11 +620,12 @@ __global__ void __launch_bounds__(EV_WARPS * 32) evaluate_kernel(EvalArgs a) {
     uint4 it = cur < n_items ? a.items[cur] : make_uint4(0, 0, 0, 0);
     bool cur_ready = false;
     unsigned long long pairs = 0, culls = 0;
+    unsigned int nfar = 0;
     while (cur < n_items) {
         const uint32_t nxt = fetch();
         const uint4 itn = nxt < n_items ? a.items[nxt] : make_uint4(0, 0, 0, 0);
         bool nxt_ready = false;
-        const uint32_t pool_off = it.x, tcount = it.y, pbeg = it.z, pcnt = it.w;
+        const uint32_t pool_off = it.x, tcount = it.y, pbeg = it.z, pcnt = it.w & 0xffu, far_cnt = it.w >> 8;
         if (tcount > 0 && !cur_ready) issue_chunk(pool_off, min(static_cast<uint32_t>(EV_CHUNK), tcount));
         const bool v0 = static_cast<uint32_t>(lane) < pcnt, v1 = static_cast<uint32_t>(lane) + 32u < pcnt;
         const float4 P0 = a.sorted[pbeg + min(static_cast<uint32_t>(lane), pcnt - 1)];
@@ -624,15 +749,70 @@ __global__ void __launch_bounds__(EV_WARPS * 32) evaluate_kernel(EvalArgs a) {
         pairs += static_cast<unsigned long long>(pcnt) * a.n_special;
         culls += static_cast<unsigned long long>(pcnt) * a.n_long;
 
+        // ---- points the near part cannot certify (noise tail): the FAR part of the tile, one point at a time with the
+        //      lanes across entries.  Entries are sorted by lb(V, c) <= dist(p, capsule(c)); the first entry whose lb
+        //      exceeds the incumbent ends the search (everything behind it, and every cylinder outside the tile, is
+        //      farther than the incumbent); an exhausted tile certifies incumbents <= D_max.
+        bool far0 = false, far1 = false;
+        {
+            const bool need0 = v0 && static_cast<uint32_t>(k0 >> 32) != 0u && !(thr_of(k0, a.slack) <= a.near);
+            const bool need1 = v1 && static_cast<uint32_t>(k1 >> 32) != 0u && !(thr_of(k1, a.slack) <= a.near);
+            const uint32_t nm0 = __ballot_sync(0xffffffffu, need0), nm1 = __ballot_sync(0xffffffffu, need1);
+            if (nm0 | nm1) {
+                const uint32_t far_off = pool_off + tcount;
+#pragma unroll 1
+                for (int k = 0; k < 2; ++k) {
+                    uint32_t mask = k ? nm1 : nm0;
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float4 Pk = k ? P1 : P0;
+                        const float px = __shfl_sync(0xffffffffu, Pk.x, src), py = __shfl_sync(0xffffffffu, Pk.y, src),
+                                    pz = __shfl_sync(0xffffffffu, Pk.z, src);
+                        unsigned long long key = __shfl_sync(0xffffffffu, k ? k1 : k0, src);
+                        float thr = thr_of(key, a.slack);                  // NaN while there is no incumbent: nothing is skipped
+                        bool cut = false;
+                        for (uint32_t base = 0; base < far_cnt; base += 32) {
+                            const uint32_t j = base + lane;
+                            const float lb = j < far_cnt ? a.tileLB[far_off + j] : __int_as_float(0x7f800000);
+                            if (__shfl_sync(0xffffffffu, lb, 0) > thr) { cut = true; break; }
+                            unsigned long long lk = KEY_NONE;
+                            const bool test = j < far_cnt && !(lb > thr);
+                            bool hit = false;
+                            if (test) {
+                                const float4 ca = a.tileA[far_off + j], cb = a.tileB[far_off + j];
+                                hit = cull_pass(px, py, pz, ca, cb, thr);
+                                if (hit) lk = make_key(eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr),
+                                                       static_cast<uint32_t>(a.tileI[far_off + j]));
+                            }
+                            culls += __popc(__ballot_sync(0xffffffffu, test));
+                            pairs += __popc(__ballot_sync(0xffffffffu, hit));
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                const unsigned long long other = __shfl_xor_sync(0xffffffffu, lk, o);
+                                lk = other < lk ? other : lk;
+                            }
+                            if (lk < key) { key = lk; thr = thr_of(key, a.slack); }
+                        }
+                        const bool ok = static_cast<uint32_t>(key >> 32) == 0u || cut || thr <= a.reach;
+                        if (lane == src) {
+                            if (k) { k1 = key; far1 = ok; } else { k0 = key; far0 = ok; }
+                        }
+                    }
+                }
+                nfar += __popc(__ballot_sync(0xffffffffu, far0)) + __popc(__ballot_sync(0xffffffffu, far1));
+            }
+        }
+
         // ---- certified points: fused winner-only epilogue, one 32-byte record at the original row;
-        //      the rest join the pending list with their incumbent ----
+        //      the rest join the pending list (ring search) with their incumbent ----
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const bool valid = k ? v1 : v0;
             const float4 P = k ? P1 : P0;
             const unsigned long long key = k ? k1 : k0;
             // NaN incumbent (hi word 0) is final: NaN beats everything.  KEY_NONE gives thr = NaN: not certified.
-            const bool done = valid && (static_cast<uint32_t>(key >> 32) == 0u || thr_of(key, a.slack) <= a.reach);
+            const bool done = valid && (static_cast<uint32_t>(key >> 32) == 0u || thr_of(key, a.slack) <= a.near || (k ? far1 : far0));
             const bool pend = valid && !done;
             if (done) {
                 const uint32_t j = key_index(key);
@@ -663,13 +843,15 @@ __global__ void __launch_bounds__(EV_WARPS * 32) evaluate_kernel(EvalArgs a) {
     if (lane == 0 && (pairs | culls)) {
         atomicAdd(&a.st->pairs_grid, pairs);
         atomicAdd(&a.st->cull_tests, culls);
+        if (nfar) atomicAdd(&a.st->far_certified, nfar);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// ring search: one warp per pending point, shells of voxels around its home voxel
+// ring search: one CTA per pending point, shells of voxels around its home voxel
 // ------------------------------------------------------------------------------------------------
 constexpr int RING_MAX = 8;
+constexpr int RING_WARPS = 8;
 
 struct RingArgs {
     const float *pts;
@@ -694,72 +876,124 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 }
 
 // All tiles of voxels V' with dist(p, box(V')) <= rho - D together hold every cylinder within rho of p (walk from
-// the cylinder's nearest point towards p by D).  After the shells 0..k every voxel with box distance < k*h has
-// been visited, so an incumbent <= D + k*h is certified.
+// the cylinder's nearest point towards p by D).  After the Chebyshev shells 0..k every voxel with box distance < k*h
+// has been visited, so an incumbent <= D + k*h is certified.  (D = D_max; shell 0, the home tile, was the tile
+// kernel's.)  With an incumbent rho the CTA therefore visits, in ONE pass, the voxels of the shells 1..ceil((rho-D)/h)
+// that lie within rho - D of the point; without one it grows the search shell by shell until something is found.
+// A pass has two block-wide steps so that no thread ever waits on a chain of dependent loads:
+//   gather:  the threads enumerate the candidate voxels, test the box distance and append {first entry, count} of the
+//            non-empty tiles to a shared list (block-wide scan of the counts);
+//   sweep:   the entries of all listed tiles form one flat index space, thread t takes entries t, t + 256, ... (binary
+//            search of the list), runs the capsule cull against its incumbent and evaluates the survivors.
+// The threads' winners meet in a warp-shuffle min and a shared 64-bit atomicMin.
+constexpr int RING_LIST = 1024;         // candidate voxels per gather step
+
 template <bool GUARD, bool NFMA>
-__global__ void __launch_bounds__(256) ring_kernel(RingArgs a, GridDev g) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridDev g) {
+    __shared__ unsigned long long s_key;
+    __shared__ uint32_t s_off[RING_LIST], s_beg[RING_LIST + 1];
+    __shared__ uint32_t s_warp[RING_WARPS];
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_pend = a.st->pending;
-    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long pairs = 0, culls = 0;
-    for (unsigned int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < n_pend; task += nwarps) {
+    for (unsigned int task = blockIdx.x; task < n_pend; task += gridDim.x) {
         const int32_t ri = a.pend_idx[task];
-        if (ri < 0) continue;                                  // outside the grid: already on the brute list
+        if (ri < 0) continue;                                  // outside the grid: already on the exhaustive list
         const float *p = a.pts + static_cast<int64_t>(ri) * a.row_stride;
         const float px = p[0], py = p[1], pz = p[2];
         const int hx = static_cast<int>((px - g.ox) * g.inv_h), hy = static_cast<int>((py - g.oy) * g.inv_h),
                   hz = static_cast<int>((pz - g.oz) * g.inv_h);
         unsigned long long key = a.pend_keys[task];
         bool certified = false;
-        for (int k = 1; k <= RING_MAX + 1; ++k) {
+        int kdone = 0;                                         // shells 0..kdone have been searched
+        for (;;) {
             const float thr = thr_of(key, g.slack);
-            if (static_cast<uint32_t>(key >> 32) == 0u || thr <= g.reach + (k - 1) * g.h) { certified = true; break; }
-            if (k > RING_MAX) break;
+            if (static_cast<uint32_t>(key >> 32) == 0u || thr <= g.reach + kdone * g.h) { certified = true; break; }
+            if (kdone >= RING_MAX) break;
             const float need_r = thr - g.reach;                // NaN while there is no incumbent: every voxel is needed
-            const int side = 2 * k + 1, total = side * side * side;
+            int ktarget = kdone + 1;
+            if (need_r == need_r) ktarget = max(ktarget, min(RING_MAX, static_cast<int>(ceilf(need_r * g.inv_h))));
+            const int side = 2 * ktarget + 1, total = side * side * side;
+            if (tid == 0) s_key = key;
             unsigned long long lk = KEY_NONE;
             float lthr = thr;
-            for (int base = 0; base < total; base += 32) {
-                const int idx = base + lane;
-                uint32_t off = 0, cnt = 0;
-                if (idx < total) {
-                    const int dx = idx % side - k, dy = (idx / side) % side - k, dz = idx / (side * side) - k;
-                    const int x = hx + dx, y = hy + dy, z = hz + dz;
-                    if (max(max(abs(dx), abs(dy)), abs(dz)) == k && x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz) {
-                        const float lx = g.ox + x * g.h, ly = g.oy + y * g.h, lz = g.oz + z * g.h;
-                        const float gx = fmaxf(fmaxf(lx - px, px - (lx + g.h)), 0.f);
-                        const float gy = fmaxf(fmaxf(ly - py, py - (ly + g.h)), 0.f);
-                        const float gz = fmaxf(fmaxf(lz - pz, pz - (lz + g.h)), 0.f);
-                        const float dbox = sqrtf(gx * gx + gy * gy + gz * gz);
-                        if (!(dbox > need_r + g.slack)) {
-                            const uint32_t code = voxel_code(g, x, y, z);
-                            cnt = a.tile_cnt[code];
-                            off = a.tile_start[code];
+            for (int chunk = 0; chunk < total; chunk += RING_LIST) {
+                // ---- gather: 4 consecutive candidates per thread
+                uint32_t off[4], cnt[4];
+                uint32_t mine = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = chunk + tid * 4 + q;
+                    off[q] = 0; cnt[q] = 0;
+                    if (idx < total) {
+                        const int dx = idx % side - ktarget, dy = (idx / side) % side - ktarget, dz = idx / (side * side) - ktarget;
+                        const int x = hx + dx, y = hy + dy, z = hz + dz;
+                        if (max(max(abs(dx), abs(dy)), abs(dz)) > kdone && x >= 0 && y >= 0 && z >= 0 && x < g.nx && y < g.ny && z < g.nz) {
+                            const float lx = g.ox + x * g.h, ly = g.oy + y * g.h, lz = g.oz + z * g.h;
+                            const float gx = fmaxf(fmaxf(lx - px, px - (lx + g.h)), 0.f);
+                            const float gy = fmaxf(fmaxf(ly - py, py - (ly + g.h)), 0.f);
+                            const float gz = fmaxf(fmaxf(lz - pz, pz - (lz + g.h)), 0.f);
+                            if (!(sqrtf(gx * gx + gy * gy + gz * gz) > need_r + g.slack)) {
+                                const uint32_t code = voxel_code(g, x, y, z);
+                                cnt[q] = a.tile_cnt[code];
+                                off[q] = a.tile_start[code];
+                            }
                         }
                     }
+                    mine += cnt[q];
                 }
-                uint32_t mask = __ballot_sync(0xffffffffu, cnt > 0);
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const uint32_t o = __shfl_sync(0xffffffffu, off, src), c = __shfl_sync(0xffffffffu, cnt, src);
-                    for (uint32_t j = lane; j < c; j += 32) {
-                        const float4 ca = a.tileA[o + j], cb = a.tileB[o + j];
-                        if (cull_pass(px, py, pz, ca, cb, lthr)) {
-                            const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr);
-                            const unsigned long long kk = make_key(d, static_cast<uint32_t>(a.tileI[o + j]));
-                            lk = kk < lk ? kk : lk;
-                            lthr = thr_of(lk < key ? lk : key, g.slack);
-                            ++pairs;
-                        }
+                // block-wide exclusive scan of the per-thread entry counts
+                uint32_t inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                if (lane == 31) s_warp[warp] = inc;
+                __syncthreads();
+                uint32_t wbase = 0;
+#pragma unroll
+                for (int w = 0; w < RING_WARPS; ++w) wbase += w < warp ? s_warp[w] : 0u;
+                uint32_t run = wbase + inc - mine;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {          // empty tiles get zero-length ranges: harmless for the search
+                    s_off[tid * 4 + q] = off[q];
+                    s_beg[tid * 4 + q] = run;
+                    run += cnt[q];
+                }
+                if (tid == RING_WARPS * 32 - 1) { s_beg[RING_LIST] = run; s_total = run; }
+                __syncthreads();
+                // ---- sweep: flat index space over the listed tiles
+                const uint32_t n_ent = s_total;
+                for (uint32_t e = tid; e < n_ent; e += RING_WARPS * 32) {
+                    int lo = 0, hi = RING_LIST;            // last slot with s_beg[slot] <= e
+#pragma unroll
+                    for (int it = 0; it < 10; ++it) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_beg[mid] <= e) lo = mid; else hi = mid;
                     }
-                    culls += (c + 31u - lane) / 32u;
+                    const uint32_t pos = s_off[lo] + (e - s_beg[lo]);
+                    const float4 ca = a.tileA[pos], cb = a.tileB[pos];
+                    ++culls;
+                    if (cull_pass(px, py, pz, ca, cb, lthr)) {
+                        const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr);
+                        const unsigned long long kk = make_key(d, static_cast<uint32_t>(a.tileI[pos]));
+                        lk = kk < lk ? kk : lk;
+                        lthr = thr_of(lk < key ? lk : key, g.slack);
+                        ++pairs;
+                    }
                 }
+                __syncthreads();                           // the lists are rewritten by the next chunk
             }
             lk = warp_min_u64(lk);
-            key = lk < key ? lk : key;
+            if (lane == 0 && lk < key) atomicMin(&s_key, lk);
+            __syncthreads();
+            key = s_key;
+            kdone = ktarget;
+            __syncthreads();
         }
-        if (lane == 0) {
+        if (tid == 0) {
             a.pend_keys[task] = key;
             if (!certified) a.brute_slots[atomicAdd(&a.st->n_brute, 1u)] = task;
         }
@@ -808,7 +1042,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     if (h->n_listed == 0 && h->n_long == 0) return label_brute(h, a);     // only special cylinders: nothing to prune with
 
     const float slack = slack_for(h->maxabs);
-    const GridDev g = to_dev(h->grid, slack, h->reach);
+    const GridDev g = to_dev(h->grid, slack, h->reach, h->near);
     const uint32_t ncodes = h->grid.ncell_codes;
     const size_t n = static_cast<size_t>(a.n);
 
@@ -817,8 +1051,6 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const size_t max_items = n / PTS_PER_ITEM + max_occ + 1;
     TM_CUDA(h, h->cell_count.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->cell_start.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
-    TM_CUDA(h, h->pt_cell.ensure(sizeof(uint32_t) * n));
-    TM_CUDA(h, h->pt_rank.ensure(sizeof(uint32_t) * n));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
     TM_CUDA(h, h->items.ensure(sizeof(uint4) * max_items));
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
@@ -833,18 +1065,17 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
 
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
     bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cell_count.as<uint32_t>(),
-                                                h->pt_cell.as<uint32_t>(), h->pt_rank.as<uint32_t>(), h->pend_idx.as<int32_t>(),
-                                                h->keys.as<unsigned long long>(), h->brute_slots.as<uint32_t>(), dst);
+                                                h->pend_idx.as<int32_t>(), h->keys.as<unsigned long long>(),
+                                                h->brute_slots.as<uint32_t>(), dst);
     TM_KCHECK(h, st, "bin_count_kernel");
     mark(h, 1, st);
     int rc = run_scan(h, h->cell_count.as<uint32_t>(), ncodes, 1, h->cell_start.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
-                      h->cyl_cell_cnt.as<uint32_t>(), h->items.as<uint4>(), dst, st);
+                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), dst, st);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
     mark(h, 2, st);
-    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, h->pt_cell.as<uint32_t>(),
-                                                  h->pt_rank.as<uint32_t>(), h->cell_start.as<uint32_t>(),
-                                                  h->sorted_pts.as<float4>());
+    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cell_count.as<uint32_t>(),
+                                                  h->cell_start.as<uint32_t>(), h->sorted_pts.as<float4>());
     TM_KCHECK(h, st, "bin_scatter_kernel");
 
     mark(h, 3, st);
@@ -860,7 +1091,8 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.long_list = h->long_list.as<int32_t>();
     ev.n_special = h->n_special; ev.n_aligned = h->n_aligned; ev.n_long = h->n_long;
     ev.atol = a.prm.perp_atol; ev.eps = a.prm.norm_eps;
-    ev.slack = slack; ev.reach = h->reach;
+    ev.tileLB = h->tileLB.as<float>();
+    ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
     ev.move_to_mantle = a.prm.move_to_mantle;
     ev.rec = h->rec.as<float4>();
     ev.pend_idx = h->pend_idx.as<int32_t>();
@@ -880,7 +1112,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
 #undef TM_EVAL_CASE
     TM_KCHECK(h, st, "evaluate_kernel");
 
-    // points the tiles could not certify: shells of neighbouring voxels, one warp per point
+    // still uncertified at D_max (beyond the far part of their own tile): shells of neighbouring voxels, one CTA per point
     mark(h, 4, st);
     RingArgs rg;
     rg.pts = a.pts; rg.row_stride = a.row_stride;
@@ -892,8 +1124,8 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
     rg.st = dst;
     const int rg_blocks = h->sm_count * 8;
-    if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, 256, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, 256, 0, st>>>(rg, g); }
-    else       { if (nfma) ring_kernel<false, true><<<rg_blocks, 256, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, 256, 0, st>>>(rg, g); }
+    if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
+    else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
 
     // exhaustive search for what is left, then the epilogue of every pending point

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TM_ABI_VERSION 2
+#define TM_ABI_VERSION 3
 
 /* status codes */
 #define TM_OK               0
@@ -80,7 +80,8 @@ typedef struct tm_params {
 typedef struct tm_stats {
     uint64_t pairs_evaluated;   /* full (point, cylinder) evaluations in reference arithmetic, all kernels   */
     uint64_t cull_tests;        /* capsule lower-bound tests that decided whether a pair is evaluated        */
-    uint64_t points_grid;       /* points certified by their own voxel's tile                                */
+    uint64_t points_grid;       /* points certified by the near part of their own voxel's tile               */
+    uint64_t points_far;        /* points certified by the far part of their own voxel's tile                */
     uint64_t points_ring;       /* points certified by the search of neighbouring voxel shells               */
     uint64_t points_brute;      /* points answered by the exhaustive kernel (outliers, brute mode)           */
     uint64_t index_entries;     /* (voxel, cylinder) entries of the static voxel index                       */
@@ -88,7 +89,8 @@ typedef struct tm_stats {
     uint32_t work_items;        /* (voxel, <=64-point slice) items processed by the tile kernel              */
     uint32_t mode_used;         /* TM_MODE_BRUTE or TM_MODE_GRID                                             */
     float    cell_size;         /* voxel edge actually used                                                  */
-    float    reach;             /* certified radius D of the tiles                                           */
+    float    reach;             /* D_max: a tile lists every cylinder within D_max of its voxel              */
+    float    near_reach;        /* D_near: radius covered by the near part of a tile (<= reach)              */
     uint32_t grid_dim[3];       /* voxel grid extent                                                         */
 } tm_stats;
 

@@ -276,8 +276,8 @@ def test_long_special_and_remote_cylinders(eng, vn):
     with np.errstate(all="ignore"):
         got2 = _label(eng, case2, pts[:20_000], "grid")
         assert_parity(got2, ora2, f"nan-row/{vn}", require_bitwise=True)
-    assert st["mode_used"] == 2 and st["points_ring"] > 0 and st["points_brute"] > 0
-    assert st["points_grid"] + st["points_ring"] + st["points_brute"] == len(pts)
+    assert st["mode_used"] == 2 and st["points_far"] > 0 and st["points_ring"] > 0 and st["points_brute"] > 0
+    assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == len(pts)
 
 
 # ---- full-size properties ---------------------------------------------------------------------------------
@@ -298,7 +298,7 @@ def test_full_size_properties(eng, n, m):
     dpts = torch.tensor(pts, device=dev)
     full = eng.label(dpts, api.VARIANT_A, mode="grid", want=("index", "id", "dist", "offset"))
     st = eng.stats()
-    assert st["mode_used"] == 2 and st["points_grid"] + st["points_ring"] + st["points_brute"] == n
+    assert st["mode_used"] == 2 and st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == n
     rng = np.random.default_rng(3)
     sub = torch.tensor(rng.choice(n, 20_000, replace=False), device=dev)
     brute = eng.label(dpts[sub], api.VARIANT_A, mode="brute", want=("index", "id", "dist", "offset"))
