@@ -1,0 +1,85 @@
+"""Drop-in for the ONE function of the reference's ``Modules/Pipeline/QSMFittingDepthFirst.py`` that sits on the
+nearest-cylinder path: ``cylinder_proximity_based_segmentation`` (reference :1006-1094), the third caller of
+``closest_cylinder_cuda_batch``.  The sphere-following QSM fit around it is out of scope.
+
+The reference runs this thousands of times per tree: a ball query on the host KD-tree, a mask intersection, then,
+per 1024 selected points, five small H2D copies, ~70 ATen launches and three synchronous D2H copies, only to keep
+``distance < eps`` (:1084).  Here the cloud is made resident on the device once (keyed on the identity of
+``points``), a call ships the selected row indices plus the raw cylinders, one kernel prepares the cylinders
+(:1043-1045), evaluates every pair in the reference's operation order and returns one flag per point
+(``tm_proximity_flags_host``).  Same signature, same return value (the updated copy of the mask).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ... import api
+from ..Projection import closest_cylinder_cuda_batch  # noqa: F401  (re-exported like the reference's import, :9)
+
+_resident: dict[int, tuple] = {}            # device index -> identity of the resident cloud
+
+
+def _cuda_device(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"cylinder_proximity_based_segmentation needs a CUDA device, got {dev}: "
+                           "the B200 path has no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _ensure_resident(eng: api.Engine, dev: torch.device, points: np.ndarray) -> None:
+    iface = points.__array_interface__
+    key = (id(points), iface["data"][0], points.shape, points.strides, points.dtype.str)
+    if _resident.get(dev.index) != key:
+        eng.upload_cloud(points[:, :3])
+        _resident[dev.index] = key
+
+
+def invalidate_resident_cloud(device=None) -> None:
+    """Forget the resident cloud (call after modifying ``points`` in place)."""
+    if device is None:
+        _resident.clear()
+    else:
+        _resident.pop(_cuda_device(device).index, None)
+
+
+def cylinder_proximity_based_segmentation(points, input_unsegmented_mask, query_sphere, cylinders, point_tree, eps,
+                                          device, batch_size=1024):
+    """Mark the unsegmented points near ``query_sphere`` that lie within ``eps`` of their closest cylinder.
+
+    points: (N, >=3) array of all points; input_unsegmented_mask: bool (N,); query_sphere: object with ``center``
+    and ``radius``; cylinders: objects with ``start``, ``end``, ``radius``, ``id``; point_tree: KD-tree over
+    ``points`` offering ``query_ball_point``.  Returns the updated COPY of the mask (reference :1094).
+    ``batch_size`` is accepted for signature compatibility; results do not depend on it.
+    """
+    del batch_size
+    dev = _cuda_device(device)
+    # reference :1033-1036 (fp64 numpy arrays, cast to fp32 by torch.tensor(..., dtype=float32) at :1039-1041)
+    start_arr = np.array([c.start for c in cylinders])
+    end_arr = np.array([c.end for c in cylinders])
+    radius_arr = np.array([c.radius for c in cylinders])
+
+    # reference :1050-1066: points within 3 sphere radii that are still unsegmented
+    local_indices = point_tree.query_ball_point(query_sphere.center, query_sphere.radius * 3)
+    if not len(local_indices):
+        return input_unsegmented_mask.copy()
+    local_indices = np.array(local_indices, dtype=int)
+    local_mask_full = np.zeros_like(input_unsegmented_mask)
+    local_mask_full[local_indices] = True
+    subset_indices = np.where(local_mask_full & input_unsegmented_mask)[0]
+    if subset_indices.size == 0:
+        return input_unsegmented_mask.copy()
+
+    eng = api.get_engine(dev)
+    points = np.asarray(points)
+    _ensure_resident(eng, dev, points)
+    # reference :1079-1084: Projection.closest_cylinder_cuda_batch (variant B) on C-contiguous tensors, unguarded
+    # axis_unit (:1045); distances_batch < eps
+    flags = eng.proximity_flags(subset_indices, start_arr.astype(np.float32), end_arr.astype(np.float32),
+                                radius_arr.astype(np.float32), eps, api.VARIANT_B, axis_eps=0.0, norm_fma=True)
+    output_mask = input_unsegmented_mask.copy()
+    output_mask[subset_indices[flags]] = False
+    return output_mask

@@ -207,6 +207,53 @@ class Engine:
             ctypes.byref(prm), out.ctypes.data, dist.ctypes.data if dist is not None else None))
         return (out, dist) if want_dist else out
 
+    # -- small-table fast path (QSMFittingDepthFirst.py:1006-1094) ---------------------------------
+    def upload_cloud(self, cloud: np.ndarray) -> None:
+        """Make a host cloud resident on the device (fp32 xyz) for ``proximity_flags``."""
+        cloud = np.asarray(cloud)
+        if cloud.ndim != 2 or cloud.shape[1] < 3:
+            raise ValueError(f"cloud must be (N, >=3), got {cloud.shape}")
+        if cloud.dtype not in (np.float32, np.float64):
+            cloud = cloud.astype(np.float64)
+        if cloud.shape[0] > 1 and (cloud.strides[1] != cloud.itemsize or cloud.strides[0] % cloud.itemsize
+                                   or cloud.strides[0] < 3 * cloud.itemsize):
+            cloud = np.ascontiguousarray(cloud)
+        n = cloud.shape[0]
+        row_stride = cloud.strides[0] // cloud.itemsize if n > 1 else max(3, cloud.shape[1])
+        self._check(self._lib.tm_cloud_upload_host(
+            self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride))
+        self._resident_n = n
+
+    def proximity_flags(self, subset, start, end, radius, eps: float, variant: Variant = VARIANT_B,
+                        axis_eps: float = 0.0, norm_fma: bool = True, want_dist: bool = False, want_index: bool = False):
+        """``distance to the closest of the given RAW cylinders < eps`` for rows ``subset`` of the resident cloud
+        (``None``: every row).  Returns ``flags`` (bool) and, on request, distances and winning rows."""
+        start = np.ascontiguousarray(np.asarray(start, dtype=np.float32).reshape(-1, 3))
+        end = np.ascontiguousarray(np.asarray(end, dtype=np.float32).reshape(-1, 3))
+        radius = np.ascontiguousarray(np.asarray(radius, dtype=np.float32).reshape(-1))
+        m = start.shape[0]
+        if end.shape[0] != m or radius.shape[0] != m:
+            raise ValueError("cylinder arrays disagree on M")
+        if subset is None:
+            n, sub_ptr = getattr(self, "_resident_n", 0), None
+        else:
+            subset = np.ascontiguousarray(np.asarray(subset, dtype=np.int64).reshape(-1))
+            n, sub_ptr = subset.shape[0], subset.ctypes.data
+        flags = np.empty(n, dtype=np.uint8)
+        dist = np.empty(n, dtype=np.float32) if want_dist else None
+        index = np.empty(n, dtype=np.int32) if want_index else None
+        prm = self._params(variant, True, norm_fma, "brute", 0.0)
+        self._check(self._lib.tm_proximity_flags_host(
+            self._h, sub_ptr, n, start.ctypes.data, end.ctypes.data, radius.ctypes.data, m, ctypes.byref(prm),
+            float(axis_eps), float(eps), flags.ctypes.data, dist.ctypes.data if want_dist else None,
+            index.ctypes.data if want_index else None))
+        out = [flags.view(np.bool_)]
+        if want_dist:
+            out.append(dist)
+        if want_index:
+            out.append(index)
+        return out[0] if len(out) == 1 else tuple(out)
+
     # -- introspection -----------------------------------------------------------------------
     def stats(self) -> dict:
         s = B.TmStats()

@@ -119,6 +119,15 @@ __global__ void f64_to_f32_xyz_kernel(const double *__restrict__ cloud, int64_t 
     }
 }
 
+__global__ void f32_xyz_kernel(const float *__restrict__ cloud, int64_t n, int64_t row_stride, float *__restrict__ out) {
+    const int64_t total = n * 3;
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = e / 3;
+        out[e] = cloud[row * row_stride + (e - row * 3)];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP32 pipe probe
 // ------------------------------------------------------------------------------------------------
@@ -232,7 +241,8 @@ int tm_destroy(tm_handle *h) {
     tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
-                          &h->pend_idx, &h->brute_slots, &h->rec, &h->dstats, &h->scratch_f};
+                          &h->pend_idx, &h->brute_slots, &h->rec, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
+                          &h->small_out};
     for (auto *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         h->chunk_in[i].release(); h->chunk_rec[i].release(); h->chunk_off[i].release(); h->chunk_id[i].release();
@@ -240,6 +250,7 @@ int tm_destroy(tm_handle *h) {
         if (h->pinned_in[i]) cudaFreeHost(h->pinned_in[i]);
         if (h->pinned_out[i]) cudaFreeHost(h->pinned_out[i]);
     }
+    if (h->small_stream) cudaStreamDestroy(h->small_stream);
     for (auto &s : h->pipe_stream) if (s) cudaStreamDestroy(s);
     for (auto &e : h->pipe_event) if (e) cudaEventDestroy(e);
     for (auto &e : h->phase_ev) if (e) cudaEventDestroy(e);
@@ -495,6 +506,105 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
     TM_CUDA(h, cudaStreamSynchronize(s_cmp));
     h->stats.pairs_evaluated = total.pairs_evaluated;
     h->stats.points_brute = total.points_brute;
+    return TM_OK;
+}
+
+// ---- small-table fast path ------------------------------------------------------------------------
+int tm_cloud_upload_host(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride) {
+    if (!h) return TM_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!cloud_host || row_stride < 3)) || (dtype != TM_F32 && dtype != TM_F64))
+        return fail(h, TM_ERR_INVALID, "tm_cloud_upload_host: bad argument%s%s");
+    TM_CUDA(h, cudaSetDevice(h->device));
+    if (!h->small_stream) TM_CUDA(h, cudaStreamCreateWithFlags(&h->small_stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->small_stream;
+    h->cloud_res_n = -1;
+    if (n == 0) { h->cloud_res_n = 0; return TM_OK; }
+    const size_t esz = dtype == TM_F32 ? 4 : 8;
+    TM_CUDA(h, h->cloud_res.ensure(sizeof(float) * 3 * static_cast<size_t>(n)));
+    if (dtype == TM_F32 && row_stride == 3) {
+        TM_CUDA(h, cudaMemcpyAsync(h->cloud_res.p, cloud_host, sizeof(float) * 3 * static_cast<size_t>(n), cudaMemcpyHostToDevice, st));
+    } else {
+        // wider rows / float64: stage the raw rows, then gather + round to fp32 on the device
+        // (torch.tensor(points, dtype=torch.float32): round to nearest even)
+        const size_t raw = static_cast<size_t>(n) * static_cast<size_t>(row_stride) * esz;
+        TM_CUDA(h, h->chunk_in[0].ensure(raw));
+        TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[0].p, cloud_host, raw, cudaMemcpyHostToDevice, st));
+        const int blocks = static_cast<int>(std::min<int64_t>((n * 3 + 255) / 256, static_cast<int64_t>(h->sm_count) * 32));
+        if (dtype == TM_F64) f64_to_f32_xyz_kernel<<<blocks, 256, 0, st>>>(h->chunk_in[0].as<double>(), n, row_stride, h->cloud_res.as<float>());
+        else f32_xyz_kernel<<<blocks, 256, 0, st>>>(h->chunk_in[0].as<float>(), n, row_stride, h->cloud_res.as<float>());
+        TM_CUDA(h, cudaGetLastError());
+    }
+    TM_CUDA(h, cudaStreamSynchronize(st));
+    h->cloud_res_n = n;
+    return TM_OK;
+}
+
+int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n, const float *start_host, const float *end_host,
+                            const float *radius_host, int64_t m, const tm_params *params, float axis_eps, float eps,
+                            uint8_t *out_flags_host, float *out_dist_host, int32_t *out_index_host) {
+    if (!h) return TM_ERR_INVALID;
+    int rc = check_params(h, params);
+    if (rc != TM_OK) return rc;
+    if (h->cloud_res_n < 0) return fail(h, TM_ERR_STATE, "tm_proximity_flags_host called before tm_cloud_upload_host%s%s");
+    if (n < 0 || m < 0) return fail(h, TM_ERR_INVALID, "tm_proximity_flags_host: negative size%s%s");
+    if (!subset_host && n > h->cloud_res_n) return fail(h, TM_ERR_INVALID, "tm_proximity_flags_host: more points than the resident cloud holds%s%s");
+    if (n == 0) return TM_OK;
+    if (m == 0) return fail(h, TM_ERR_NO_CYLINDERS, "%s%s", tm_status_string(TM_ERR_NO_CYLINDERS));
+    if (m > tmn::SMALL_MAX_M) return fail(h, TM_ERR_INVALID, "tm_proximity_flags_host: too many cylinders for the small-table path%s%s");
+    if (!start_host || !end_host || !radius_host) return fail(h, TM_ERR_INVALID, "tm_proximity_flags_host: null cylinder array%s%s");
+    TM_CUDA(h, cudaSetDevice(h->device));
+    if (!h->small_stream) TM_CUDA(h, cudaStreamCreateWithFlags(&h->small_stream, cudaStreamNonBlocking));
+    cudaStream_t st = h->small_stream;
+    if (subset_host)
+        for (int64_t i = 0; i < n; ++i)
+            if (subset_host[i] < 0 || subset_host[i] >= h->cloud_res_n)
+                return fail(h, TM_ERR_INVALID, "tm_proximity_flags_host: subset index outside the resident cloud%s%s");
+
+    // one staging block per direction: [subset rows | cylinders] in, [dist | index | flags] out
+    const size_t idx_bytes = subset_host ? sizeof(int64_t) * static_cast<size_t>(n) : 0;
+    const size_t cyl_bytes = sizeof(float) * 7 * static_cast<size_t>(m);
+    TM_CUDA(h, h->small_in.ensure(idx_bytes + cyl_bytes));
+    TM_CUDA(h, h->small_out.ensure(static_cast<size_t>(n) * 9 + 16));
+    if (h->pinned_in_cap < idx_bytes + cyl_bytes || !h->pinned_in[0]) {
+        if (h->pinned_in[0]) { cudaFreeHost(h->pinned_in[0]); h->pinned_in[0] = nullptr; }
+        if (h->pinned_in[1]) { cudaFreeHost(h->pinned_in[1]); h->pinned_in[1] = nullptr; }
+        h->pinned_in_cap = 0;
+        const size_t want = std::max<size_t>(idx_bytes + cyl_bytes, 1 << 20);
+        TM_CUDA(h, cudaMallocHost(&h->pinned_in[0], want));
+        TM_CUDA(h, cudaMallocHost(&h->pinned_in[1], want));
+        h->pinned_in_cap = want;
+    }
+    unsigned char *stage = static_cast<unsigned char *>(h->pinned_in[0]);
+    if (subset_host) memcpy(stage, subset_host, idx_bytes);
+    float *cyl = reinterpret_cast<float *>(stage + idx_bytes);
+    for (int64_t c = 0; c < m; ++c) {
+        cyl[7 * c + 0] = start_host[3 * c]; cyl[7 * c + 1] = start_host[3 * c + 1]; cyl[7 * c + 2] = start_host[3 * c + 2];
+        cyl[7 * c + 3] = end_host[3 * c];   cyl[7 * c + 4] = end_host[3 * c + 1];   cyl[7 * c + 5] = end_host[3 * c + 2];
+        cyl[7 * c + 6] = radius_host[c];
+    }
+    TM_CUDA(h, cudaMemcpyAsync(h->small_in.p, stage, idx_bytes + cyl_bytes, cudaMemcpyHostToDevice, st));
+
+    tmn::SmallArgs a;
+    a.cloud = h->cloud_res.as<float>();
+    a.subset = subset_host ? h->small_in.as<int64_t>() : nullptr;
+    a.n = n;
+    a.cyl = reinterpret_cast<const float *>(h->small_in.as<unsigned char>() + idx_bytes);
+    a.m = static_cast<int>(m);
+    a.axis_eps = axis_eps; a.atol = params->perp_atol; a.eps_norm = params->norm_eps; a.eps_flag = eps;
+    unsigned char *ob = h->small_out.as<unsigned char>();
+    a.dist = out_dist_host ? reinterpret_cast<float *>(ob) : nullptr;
+    a.index = out_index_host ? reinterpret_cast<int32_t *>(ob + 4 * static_cast<size_t>(n)) : nullptr;
+    a.flags = out_flags_host ? ob + 8 * static_cast<size_t>(n) : nullptr;
+    rc = tmn::run_proximity(h, a, params->norm_eps > 0.f, params->norm_fma != 0, st);
+    if (rc != TM_OK) return rc;
+    if (out_dist_host) TM_CUDA(h, cudaMemcpyAsync(out_dist_host, a.dist, 4 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+    if (out_index_host) TM_CUDA(h, cudaMemcpyAsync(out_index_host, a.index, 4 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+    if (out_flags_host) TM_CUDA(h, cudaMemcpyAsync(out_flags_host, a.flags, static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+    TM_CUDA(h, cudaStreamSynchronize(st));
+    h->stats = tm_stats{};
+    h->stats.mode_used = TM_MODE_BRUTE;
+    h->stats.pairs_evaluated = static_cast<uint64_t>(n) * static_cast<uint64_t>(m);
+    h->stats.points_brute = static_cast<uint64_t>(n);
     return TM_OK;
 }
 

@@ -113,6 +113,13 @@ struct tm_handle {
     size_t pinned_in_cap = 0, pinned_out_cap = 0;
     tmn::DevBuf chunk_in[2], chunk_rec[2], chunk_off[2], chunk_id[2], chunk_dist[2];
 
+    // ---- small-table fast path (tm_cloud_upload_host / tm_proximity_flags_host) ----
+    tmn::DevBuf cloud_res;           // resident (n,3) fp32 copy of the caller's cloud
+    int64_t cloud_res_n = -1;
+    tmn::DevBuf small_in;            // per call: subset rows (int64) | cylinders (7 floats each)
+    tmn::DevBuf small_out;           // per call: flags (u8) | dist (f32) | index (i32)
+    cudaStream_t small_stream = nullptr;
+
     // ---- optional phase timing ----
     bool profiling = false;
     cudaEvent_t phase_ev[TM_PHASES + 1] = {nullptr};
@@ -178,6 +185,20 @@ int label_brute(tm_handle *h, const LabelArgs &a);
 // grid mode, after the voxel-tile and ring kernels: exhaustive search (with the capsule cull) for the pending
 // slots listed in h->brute_slots, then the winner-only epilogue for EVERY pending slot into h->rec
 int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, float slack, float maxabs);
+// tm_small.cu
+constexpr int SMALL_MAX_M = 3072;     // cylinders per call of the small-table kernel (2 x 16 B of shared memory each)
+struct SmallArgs {
+    const float *cloud;            // resident (n_cloud, 3) fp32
+    const int64_t *subset;         // rows to process (nullptr: rows 0..n-1)
+    int64_t n;
+    const float *cyl;              // m rows of 7 floats: start xyz, end xyz, radius
+    int m;
+    float axis_eps, atol, eps_norm, eps_flag;
+    uint8_t *flags;
+    float *dist;
+    int32_t *index;
+};
+int run_proximity(tm_handle *h, const SmallArgs &a, bool guard, bool nfma, cudaStream_t st);
 // tm_grid.cu
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream);
 int label_grid(tm_handle *h, const LabelArgs &a);

@@ -161,6 +161,27 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t cloud_dtyp
                         int64_t cloud_row_stride, const tm_params *params,
                         double *out_records_host, float *out_dist_host);
 
+/*
+ * Small-table fast path — the call pattern of cylinder_proximity_based_segmentation
+ * (Modules/Pipeline/QSMFittingDepthFirst.py:1006-1094): thousands of calls per tree, each against the few
+ * cylinders fitted last and a subset of the SAME cloud, keeping one bit per point (:1084).
+ *
+ * tm_cloud_upload_host: make an (n, >=3) TM_F32 / TM_F64 host cloud resident on the device as fp32 xyz
+ *   (torch.tensor(points, dtype=torch.float32), :1076-1079 via Projection.py:33).  Synchronous.
+ * tm_proximity_flags_host: for the rows `subset_host[0..n)` of the resident cloud (NULL: rows 0..n-1) and m RAW
+ *   cylinders (start (m,3), end (m,3), radius (m,), fp32 host arrays): prepares the cylinders as :1043-1045 does
+ *   (axis_eps 0) or as Projection.py:126-132 does (axis_eps 1e-8), runs closest_cylinder_cuda_batch with `params`
+ *   (mode / cell_size ignored: every pair is evaluated) and returns, per row, out_flags = (distance < eps) (:1084),
+ *   and optionally the distance and the winning cylinder row.  Any output may be NULL.  One H2D copy, one kernel,
+ *   one D2H copy per output; synchronous.  m is limited to 3072; larger tables go through tm_set_cylinders.
+ */
+int tm_cloud_upload_host(tm_handle *h, const void *cloud_host, int32_t cloud_dtype, int64_t n,
+                         int64_t cloud_row_stride);
+int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
+                            const float *start_host, const float *end_host, const float *radius_host, int64_t m,
+                            const tm_params *params, float axis_eps, float eps,
+                            uint8_t *out_flags_host, float *out_dist_host, int32_t *out_index_host);
+
 /* Counters of the last labelling call.  Synchronises the device. */
 int tm_get_stats(tm_handle *h, tm_stats *out);
 

@@ -20,8 +20,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+OTHER_FIXTURES = {"proximity", "features"}      # fixtures of other entry points, with their own tests
+
+
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Golden vectors of the labelling path (tests/golden/make_golden.py)."""
+    names = (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in names if n not in OTHER_FIXTURES)
 
 
 def load_golden(name):
