@@ -131,7 +131,7 @@ def cpu_sample_size(target_s: float, qsm, pts, variant) -> tuple[int, float]:
     from treemorph_b200 import synth
     arrs = synth.cylinder_arrays(qsm, variant.axis_eps)
     t0 = time.perf_counter()
-    oracle.label(pts[:2000], *_oracle_args(arrs), variant)
+    oracle.label(pts[:2000], *_oracle_args(arrs), variant, threads=host_threads())
     dt = time.perf_counter() - t0
     n = int(min(len(pts), max(2000, 2000 * target_s / max(dt, 1e-4))))
     return n, dt
@@ -142,10 +142,19 @@ def _oracle_args(arrs):
     return start, radius, length, unit, ids
 
 
+def host_threads() -> int:
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: ask the OS instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_cpu(qsm, pts, n_sample: int, threads: int = 0):
     from oracle import oracle
     from treemorph_b200 import synth
     arrs = synth.cylinder_arrays(qsm)
+    threads = threads or host_threads()
     t0 = time.perf_counter()
     res = oracle.label(pts[:n_sample], *_oracle_args(arrs), oracle.VARIANT_A, threads=threads)
     return time.perf_counter() - t0, res
@@ -166,7 +175,7 @@ def reference_arm(args):
         dt, _ = run_cpu(qsm, pts, n_s)
         total += dt
     value = n_s * args.steps / total
-    cores = oracle.max_threads()
+    cores = host_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -231,6 +240,8 @@ def main():
         start, radius, length, unit, ids = synth.cylinder_arrays(qsm)
         table = sharding.pack_table(torch.tensor(start), torch.tensor(radius), torch.tensor(length), torch.tensor(unit),
                                     torch.tensor(ids)).to(dev)
+    if world > 1:
+        dist.barrier()                      # communicator set-up is not part of the broadcast being timed
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -335,7 +346,7 @@ def main():
     # ---- rooflines
     hbm_peak, peak_kind = load_peaks()
     fp32_peak = eng.fp32_peak()
-    dom = max(("evaluate", "ring", "exhaustive", "finalize", "bin", "scatter", "scan", "unpack"), key=lambda k: phases.get(k, 0.0))
+    dom = max(("evaluate", "ring", "exhaustive", "pending", "bin", "scatter", "scan", "epilogue"), key=lambda k: phases.get(k, 0.0))
     dom_ms = phases.get(dom, 0.0) or ms_per_step
     achieved_gbs = BYTES_PER_POINT * N_POINTS / (dom_ms * 1e-3) / 1e9
     pairs = stats["pairs_evaluated"]
@@ -371,11 +382,11 @@ def main():
         n_s, _ = cpu_sample_size(12.0, qsm, pts_host, oracle.VARIANT_A)
         dt, res = run_cpu(qsm, pts_host, n_s)
         same = bool((res["id"] == out["id"][:n_s].cpu().numpy()).all())
-        cpu = {"value": n_s / dt, "unit": UNIT, "cores": oracle.max_threads(), "kind": "port",
-               "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {oracle.max_threads()} threads "
+        cpu = {"value": n_s / dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
+               "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {host_threads()} threads "
                          f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
 
-    launches_per_step = {"grid": 10, "auto": 10, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, ring, exhaustive, finalize, unpack
+    launches_per_step = {"grid": 10, "auto": 10, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, ring, exhaustive, pending winners, epilogue
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

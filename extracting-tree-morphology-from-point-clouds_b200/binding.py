@@ -15,7 +15,7 @@ TM_MODE_AUTO, TM_MODE_BRUTE, TM_MODE_GRID = 0, 1, 2
 TM_F32, TM_F64 = 0, 1
 ABI_VERSION = 3
 TM_PHASES = 9
-PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "ring", "exhaustive", "finalize", "unpack", "total")
+PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "ring", "exhaustive", "pending", "epilogue", "total")
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 

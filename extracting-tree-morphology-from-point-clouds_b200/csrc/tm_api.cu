@@ -241,7 +241,7 @@ int tm_destroy(tm_handle *h) {
     tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
-                          &h->pend_idx, &h->brute_slots, &h->rec, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
+                          &h->pend_idx, &h->brute_slots, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
                           &h->small_out};
     for (auto *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {

@@ -121,7 +121,7 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
                 const float4 *__restrict__ recA, const float4 *__restrict__ recB, const int32_t *__restrict__ ids,
                 float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index,
                 int32_t *__restrict__ out_id, float *__restrict__ out_dist, float *__restrict__ out_offset,
-                float *__restrict__ out_radius, float4 *__restrict__ rec) {
+                float *__restrict__ out_radius) {
     const int64_t n_eff = d_count ? static_cast<int64_t>(*d_count) : n;
     for (int64_t slot = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; slot < n_eff;
          slot += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -134,7 +134,6 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
         eval_pair<GUARD, NFMA, true>(px, py, pz, a, b, atol, eps, &g);
         float ox, oy, oz;
         mantle_offset<NFMA>(g, px, py, pz, move_to_mantle != 0, ox, oy, oz);
-        if (rec) { store_record(rec, row, j, ids[j], g.dist, ox, oy, oz, b.w); continue; }
         if (out_index) out_index[row] = static_cast<int32_t>(j);
         if (out_id) out_id[row] = ids[j];
         if (out_dist) out_dist[row] = g.dist;
@@ -295,7 +294,7 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
     finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, n_launch, a.row_stride, sel, d_count, keys, A, B,     \
                                                        h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
                                                        a.prm.move_to_mantle, a.out_index, a.out_id, a.out_dist,     \
-                                                       a.out_offset, a.out_radius, nullptr)
+                                                       a.out_offset, a.out_radius)
     if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
     else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
 #undef TM_FIN_CASE
@@ -312,8 +311,79 @@ int label_brute(tm_handle *h, const LabelArgs &a) {
     return TM_OK;
 }
 
-int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, float slack, float maxabs) {
-    (void)slack;
+// winning rows of the pending slots (ring-certified and exhaustive alike) -> win[original row]
+__global__ void __launch_bounds__(256) pending_winner_kernel(const int32_t *__restrict__ pend_idx, const unsigned int *__restrict__ d_count,
+                                                             const unsigned long long *__restrict__ keys, int32_t *__restrict__ win) {
+    const unsigned int n = *d_count;
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x)
+        win[pend_idx[slot] & 0x7fffffff] = static_cast<int32_t>(key_index(keys[slot]));
+}
+
+// Streaming winner-only epilogue (A:92-109) over the rows in input order: recompute the winning pair with full geometry
+// (bit-identical distance), move to the mantle, gather the ID.  Reads 12 + 4 bytes per point, writes the outputs; the
+// 16-byte cylinder records come from L1/L2 (neighbouring rows of a sorted scan line mostly share their winner, random
+// rows still hit the 1.6 MB table in L2).
+template <bool GUARD, bool NFMA>
+__global__ void __launch_bounds__(256)
+finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, const int32_t *__restrict__ win,
+                     const float4 *__restrict__ recA, const float4 *__restrict__ recB, const int32_t *__restrict__ ids,
+                     float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index, int32_t *__restrict__ out_id,
+                     float *__restrict__ out_dist, float *__restrict__ out_offset, float *__restrict__ out_radius) {
+    // two rows per thread and iteration: both rows' loads (point, winning row, then the dependent record gathers) are in
+    // flight together, which is what hides the L2 latency of the gathers
+    constexpr int R = 2;
+    const int64_t span = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t row0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; row0 < n; row0 += R * span) {
+        int64_t row[R];
+        bool ok[R];
+        uint32_t j[R];
+        float px[R], py[R], pz[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            row[k] = row0 + k * span;
+            ok[k] = row[k] < n;
+            const int64_t r = ok[k] ? row[k] : row0;
+            j[k] = static_cast<uint32_t>(win[r]);
+            const float *p = pts + r * row_stride;
+            px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+        }
+        float4 a[R], b[R];
+        int32_t id[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) { a[k] = recA[j[k]]; b[k] = recB[j[k]]; id[k] = ids[j[k]]; }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            PairGeom g;
+            eval_pair<GUARD, NFMA, true>(px[k], py[k], pz[k], a[k], b[k], atol, eps, &g);
+            float ox, oy, oz;
+            mantle_offset<NFMA>(g, px[k], py[k], pz[k], move_to_mantle != 0, ox, oy, oz);
+            if (!ok[k]) continue;
+            const int64_t r = row[k];
+            if (out_index && out_index != win) out_index[r] = static_cast<int32_t>(j[k]);
+            if (out_id) out_id[r] = id[k];
+            if (out_dist) out_dist[r] = g.dist;
+            if (out_offset) { out_offset[3 * r] = ox; out_offset[3 * r + 1] = oy; out_offset[3 * r + 2] = oz; }
+            if (out_radius) out_radius[r] = b[k].w;
+        }
+    }
+}
+
+int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win) {
+    const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
+    const int grid = static_cast<int>(std::min<int64_t>((a.n + 511) / 512, static_cast<int64_t>(h->sm_count) * 16));
+#define TM_FINR_CASE(G, F)                                                                                          \
+    finalize_rows_kernel<G, F><<<grid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, win, h->recA.as<float4>(),      \
+                                                           h->recB.as<float4>(), h->ids.as<int32_t>(), a.prm.perp_atol, \
+                                                           a.prm.norm_eps, a.prm.move_to_mantle, a.out_index, a.out_id, \
+                                                           a.out_dist, a.out_offset, a.out_radius)
+    if (guard) { if (nfma) TM_FINR_CASE(true, true); else TM_FINR_CASE(true, false); }
+    else       { if (nfma) TM_FINR_CASE(false, true); else TM_FINR_CASE(false, false); }
+#undef TM_FINR_CASE
+    TM_KCHECK(h, a.stream, "finalize_rows_kernel");
+    return TM_OK;
+}
+
+int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win, float maxabs) {
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
     BruteCullArgs b;
     b.pts = a.pts; b.row_stride = a.row_stride;
@@ -332,18 +402,9 @@ int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, float slack,
     else       { if (nfma) brute_cull_kernel<false, true><<<wgrid, 256, 0, a.stream>>>(b); else brute_cull_kernel<false, false><<<wgrid, 256, 0, a.stream>>>(b); }
     TM_KCHECK(h, a.stream, "brute_cull_kernel");
     mark(h, 6, a.stream);
-    // winner-only epilogue of EVERY pending slot (ring-certified and exhaustive alike) into the record buffer
-    const int fgrid = h->sm_count * 8;
-#define TM_FIN_CASE(G, F)                                                                                          \
-    finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, h->pend_idx.as<int32_t>(), &dst->pending,  \
-                                                       h->keys.as<unsigned long long>(), b.recA, b.recB,            \
-                                                       h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
-                                                       a.prm.move_to_mantle, nullptr, nullptr, nullptr, nullptr,    \
-                                                       nullptr, h->rec.as<float4>())
-    if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
-    else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
-#undef TM_FIN_CASE
-    TM_KCHECK(h, a.stream, "finalize_kernel (pending)");
+    pending_winner_kernel<<<h->sm_count * 4, 256, 0, a.stream>>>(h->pend_idx.as<int32_t>(), &dst->pending,
+                                                                h->keys.as<unsigned long long>(), win);
+    TM_KCHECK(h, a.stream, "pending_winner_kernel");
     return TM_OK;
 }
 

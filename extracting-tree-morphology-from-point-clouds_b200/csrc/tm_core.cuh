@@ -101,7 +101,7 @@ struct tm_handle {
     tmn::DevBuf items;               // uint4 per work item
     tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)
     tmn::DevBuf brute_slots;         // uint32 pending slots that need the exhaustive kernel
-    tmn::DevBuf rec;                 // 2 x float4 per point: {row index, id, dist, ox} {oy, oz, radius, 0}
+    tmn::DevBuf win;                 // int32 per point: winning cylinder row (when the caller passes no out_index)
     tmn::DevBuf dstats;              // tmn::DevStats + cursors
     tmn::DevBuf scratch_f;           // misc float scratch
 
@@ -183,8 +183,10 @@ struct LabelArgs {
 // tm_brute.cu
 int label_brute(tm_handle *h, const LabelArgs &a);
 // grid mode, after the voxel-tile and ring kernels: exhaustive search (with the capsule cull) for the pending
-// slots listed in h->brute_slots, then the winner-only epilogue for EVERY pending slot into h->rec
-int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, float slack, float maxabs);
+// slots listed in h->brute_slots, then the winning row of EVERY pending slot goes to win[original row]
+int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win, float maxabs);
+// streaming winner-only epilogue over all rows: win[row] -> index / id / distance / offset / radius
+int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win);
 // tm_small.cu
 constexpr int SMALL_MAX_M = 3072;     // cylinders per call of the small-table kernel (2 x 16 B of shared memory each)
 struct SmallArgs {

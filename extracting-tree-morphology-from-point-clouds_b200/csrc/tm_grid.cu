@@ -14,13 +14,14 @@
 //                runs with full lanes.  Winners are merged with a 64-bit (distance, index) atomicMin in shared
 //                memory, which is torch.argmin's comparator.
 //                A point whose best distance is <= D_near is CERTIFIED: every cylinder that could beat or tie it has
-//                lb <= D_near for the point's voxel, i.e. sits in the near part.  Its label + offset are written by
-//                the fused winner-only epilogue as one 32-byte record at the original row.
+//                lb <= D_near for the point's voxel, i.e. sits in the near part.  The winning row is stored at the
+//                point's original row (4 bytes, L2 resident).
 //                The few points that are not certified (noise tail) then walk the FAR part of the tile, lanes across
 //                entries in ascending lb order, and stop at the first entry whose lb exceeds their incumbent.
 //     ring:      points still uncertified at D_max search the tiles of the surrounding voxel shells, one CTA per point.
 //     brute:     points outside the grid / not certified within RING_MAX shells: exhaustive search with the same cull.
-//     unpack:    records --> the caller's output arrays, coalesced.
+//     epilogue:  streaming pass over the rows in input order: recompute the winning pair with full geometry, move to the
+//                mantle, gather the ID, write label + offset (coalesced reads and writes).
 //
 // Exactness: dist_ref(p,c) >= dist(p, capsule(c)) >= lb(V,c) for p in V; the cull, the lb order and
 // the certification only ever discard cylinders whose capsule is farther than the incumbent (plus a rounding
@@ -574,15 +575,14 @@ struct EvalArgs {
     uint32_t n_special, n_aligned, n_long;
     const float *tileLB;
     float atol, eps, slack, near, reach;
-    int move_to_mantle;
-    float4 *rec;
+    int32_t *win;                 // winning cylinder row of every certified point, at the point's original row
     int32_t *pend_idx;
     unsigned long long *pend_keys;
     DevStats *st;
 };
 
 template <bool GUARD, bool NFMA>
-__global__ void __launch_bounds__(EV_WARPS * 32) evaluate_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) {
     extern __shared__ __align__(128) unsigned char ev_smem[];
     WarpStage *stages = reinterpret_cast<WarpStage *>(ev_smem);
     uint64_t *bars = reinterpret_cast<uint64_t *>(ev_smem + sizeof(WarpStage) * EV_WARPS);
@@ -804,8 +804,9 @@ __global__ void __launch_bounds__(EV_WARPS * 32) evaluate_kernel(EvalArgs a) {
             }
         }
 
-        // ---- certified points: fused winner-only epilogue, one 32-byte record at the original row;
-        //      the rest join the pending list (ring search) with their incumbent ----
+        // ---- certified points: the winning row goes to the point's ORIGINAL row (a 4-byte scatter into an array that
+        //      stays L2 resident); the streaming epilogue kernel turns rows into labels + offsets with coalesced
+        //      reads and writes.  The rest join the pending list (ring search) with their incumbent ----
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const bool valid = k ? v1 : v0;
@@ -814,15 +815,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32) evaluate_kernel(EvalArgs a) {
             // NaN incumbent (hi word 0) is final: NaN beats everything.  KEY_NONE gives thr = NaN: not certified.
             const bool done = valid && (static_cast<uint32_t>(key >> 32) == 0u || thr_of(key, a.slack) <= a.near || (k ? far1 : far0));
             const bool pend = valid && !done;
-            if (done) {
-                const uint32_t j = key_index(key);
-                const float4 ca = a.recA[j], cb = a.recB[j];
-                PairGeom gm;
-                eval_pair<GUARD, NFMA, true>(P.x, P.y, P.z, ca, cb, a.atol, a.eps, &gm);
-                float ox, oy, oz;
-                mantle_offset<NFMA>(gm, P.x, P.y, P.z, a.move_to_mantle != 0, ox, oy, oz);
-                store_record(a.rec, static_cast<int64_t>(__float_as_int(P.w)), j, a.ids[j], gm.dist, ox, oy, oz, cb.w);
-            }
+            if (done) a.win[__float_as_int(P.w)] = static_cast<int32_t>(key_index(key));
             const uint32_t pm = __ballot_sync(0xffffffffu, pend);
             if (pm) {
                 unsigned int base = 0;
@@ -1010,23 +1003,6 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
 }
 
 // ------------------------------------------------------------------------------------------------
-// records --> the caller's arrays (coalesced)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) unpack_kernel(const float4 *__restrict__ rec, int64_t n, int32_t *__restrict__ out_index,
-                                                     int32_t *__restrict__ out_id, float *__restrict__ out_dist,
-                                                     float *__restrict__ out_offset, float *__restrict__ out_radius) {
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float4 r0 = rec[2 * i], r1 = rec[2 * i + 1];
-        if (out_index) out_index[i] = __float_as_int(r0.x);
-        if (out_id) out_id[i] = __float_as_int(r0.y);
-        if (out_dist) out_dist[i] = r0.z;
-        if (out_offset) { out_offset[3 * i] = r0.w; out_offset[3 * i + 1] = r1.x; out_offset[3 * i + 2] = r1.y; }
-        if (out_radius) out_radius[i] = r1.z;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
 int label_grid(tm_handle *h, const LabelArgs &a) {
@@ -1056,7 +1032,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
     TM_CUDA(h, h->brute_slots.ensure(sizeof(uint32_t) * n));
     TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * n));
-    TM_CUDA(h, h->rec.ensure(sizeof(float4) * 2 * n));
+    if (!a.out_index) TM_CUDA(h, h->win.ensure(sizeof(int32_t) * n));
     TM_CUDA(h, h->dstats.ensure(sizeof(DevStats) + 64));
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
@@ -1085,7 +1061,6 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.sorted = h->sorted_pts.as<float4>();
     ev.tileA = h->tileA.as<float4>(); ev.tileB = h->tileB.as<float4>(); ev.tileI = h->tileI.as<int32_t>();
     ev.recA = h->recA.as<float4>(); ev.recB = h->recB.as<float4>();
-    ev.ids = h->ids.as<int32_t>();
     ev.special = h->special.as<int32_t>();
     ev.aligned = h->aligned.as<int32_t>();
     ev.long_list = h->long_list.as<int32_t>();
@@ -1093,8 +1068,8 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.atol = a.prm.perp_atol; ev.eps = a.prm.norm_eps;
     ev.tileLB = h->tileLB.as<float>();
     ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
-    ev.move_to_mantle = a.prm.move_to_mantle;
-    ev.rec = h->rec.as<float4>();
+    int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();       // the caller's index array doubles as the scatter target
+    ev.win = win;
     ev.pend_idx = h->pend_idx.as<int32_t>();
     ev.pend_keys = h->keys.as<unsigned long long>();
     ev.st = dst;
@@ -1130,14 +1105,12 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
 
     // exhaustive search for what is left, then the epilogue of every pending point
     mark(h, 5, st);
-    rc = finish_pending(h, a, dst, slack, h->maxabs);
+    rc = finish_pending(h, a, dst, win, h->maxabs);
     if (rc != TM_OK) return rc;
 
+    // winner-only epilogue of every row: label + offset, streaming
     mark(h, 7, st);
-    unpack_kernel<<<pt_blocks, 256, 0, st>>>(h->rec.as<float4>(), a.n, a.out_index, a.out_id, a.out_dist, a.out_offset,
-                                             a.out_radius);
-    TM_KCHECK(h, st, "unpack_kernel");
-    return TM_OK;
+    return finalize_rows(h, a, win);
 }
 
 }  // namespace tmn

@@ -189,9 +189,9 @@ int tm_get_stats(tm_handle *h, tm_stats *out);
  * Per-phase device timing of tm_label_points (CUDA events recorded on the caller's stream between the
  * phases; off by default).  tm_get_phase_ms synchronises and fills out[0..TM_PHASES):
  *   [0] bin points into voxels   [1] voxel scan + work items   [2] scatter into voxel order
- *   [3] tile kernel: cull + dense evaluation + fused record write   [4] ring search of uncertified points
- *   [5] exhaustive kernel (brute mode, or the grid's outliers)   [6] winner epilogue of pending / brute points
- *   [7] records -> output arrays   [8] whole call
+ *   [3] tile kernel: cull + dense evaluation, winning row -> original row   [4] ring search of uncertified points
+ *   [5] exhaustive kernel (brute mode, or the grid's outliers)   [6] winning rows of the pending points (brute mode: the
+ *   winner epilogue)   [7] streaming winner epilogue: rows -> label + offset arrays   [8] whole call
  * Phases that did not run report 0.
  */
 #define TM_PHASES 9
