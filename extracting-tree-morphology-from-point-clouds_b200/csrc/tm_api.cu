@@ -49,7 +49,8 @@ __device__ __forceinline__ int float_to_ordered(float f) {
 __global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64_t s_cs, const float *__restrict__ unit,
                             int64_t u_rs, int64_t u_cs, const float *__restrict__ length, int64_t l_s,
                             const float *__restrict__ radius, int64_t r_s, const int32_t *__restrict__ ids, int64_t i_s,
-                            int m, float4 *__restrict__ recA, float4 *__restrict__ recB, int32_t *__restrict__ out_ids,
+                            int m, float4 *__restrict__ recA, float4 *__restrict__ recB, float4 *__restrict__ recAB,
+                            int32_t *__restrict__ out_ids,
                             float4 *__restrict__ boxlo, float4 *__restrict__ boxhi, int *__restrict__ bbox,
                             int32_t *__restrict__ special, int32_t *__restrict__ aligned) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,6 +60,8 @@ __global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64
     const float len = length[c * l_s], rad = radius[c * r_s];
     recA[c] = make_float4(sx, sy, sz, len);
     recB[c] = make_float4(ux, uy, uz, rad);
+    recAB[2 * c] = make_float4(sx, sy, sz, len);
+    recAB[2 * c + 1] = make_float4(ux, uy, uz, rad);
     out_ids[c] = ids ? ids[c * i_s] : c;
     const bool finite = isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(ux) && isfinite(uy) && isfinite(uz) &&
                         isfinite(len) && isfinite(rad);
@@ -238,7 +241,7 @@ int tm_destroy(tm_handle *h) {
     if (!h) return TM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
+    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->recAB, &h->cells, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
                           &h->pend_idx, &h->brute_slots, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
@@ -291,6 +294,7 @@ int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_c
     const size_t mm = static_cast<size_t>(m);
     TM_CUDA(h, h->recA.ensure(sizeof(float4) * mm));
     TM_CUDA(h, h->recB.ensure(sizeof(float4) * mm));
+    TM_CUDA(h, h->recAB.ensure(sizeof(float4) * 2 * mm));
     TM_CUDA(h, h->ids.ensure(sizeof(int32_t) * mm));
     TM_CUDA(h, h->boxlo.ensure(sizeof(float4) * mm));
     TM_CUDA(h, h->boxhi.ensure(sizeof(float4) * mm));
@@ -303,7 +307,8 @@ int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_c
     TM_CUDA(h, cudaMemcpyAsync(h->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const int blocks = static_cast<int>((m + 127) / 128);
     pack_kernel<<<blocks, 128, 0, st>>>(start, s_rs, s_cs, unit, u_rs, u_cs, length, l_s, radius, r_s, ids, i_s,
-                                        static_cast<int>(m), h->recA.as<float4>(), h->recB.as<float4>(), h->ids.as<int32_t>(),
+                                        static_cast<int>(m), h->recA.as<float4>(), h->recB.as<float4>(), h->recAB.as<float4>(),
+                                        h->ids.as<int32_t>(),
                                         h->boxlo.as<float4>(), h->boxhi.as<float4>(), h->bbox.as<int>(),
                                         h->special.as<int32_t>(), h->aligned.as<int32_t>());
     TM_CUDA(h, cudaGetLastError());

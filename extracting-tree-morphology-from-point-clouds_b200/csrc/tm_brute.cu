@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) pending_winner_kernel(const int32_t *__re
 template <bool GUARD, bool NFMA>
 __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, const int32_t *__restrict__ win,
-                     const float4 *__restrict__ recA, const float4 *__restrict__ recB, const int32_t *__restrict__ ids,
+                     const float4 *__restrict__ recAB, const int32_t *__restrict__ ids,
                      float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index, int32_t *__restrict__ out_id,
                      float *__restrict__ out_dist, float *__restrict__ out_offset, float *__restrict__ out_radius) {
     // two rows per thread and iteration: both rows' loads (point, winning row, then the dependent record gathers) are in
@@ -350,7 +350,7 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
         float4 a[R], b[R];
         int32_t id[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) { a[k] = recA[j[k]]; b[k] = recB[j[k]]; id[k] = ids[j[k]]; }
+        for (int k = 0; k < R; ++k) { a[k] = recAB[2 * j[k]]; b[k] = recAB[2 * j[k] + 1]; id[k] = out_id ? ids[j[k]] : 0; }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             PairGeom g;
@@ -372,8 +372,8 @@ int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win) {
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
     const int grid = static_cast<int>(std::min<int64_t>((a.n + 511) / 512, static_cast<int64_t>(h->sm_count) * 16));
 #define TM_FINR_CASE(G, F)                                                                                          \
-    finalize_rows_kernel<G, F><<<grid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, win, h->recA.as<float4>(),      \
-                                                           h->recB.as<float4>(), h->ids.as<int32_t>(), a.prm.perp_atol, \
+    finalize_rows_kernel<G, F><<<grid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, win, h->recAB.as<float4>(),     \
+                                                           h->ids.as<int32_t>(), a.prm.perp_atol,                       \
                                                            a.prm.norm_eps, a.prm.move_to_mantle, a.out_index, a.out_id, \
                                                            a.out_dist, a.out_offset, a.out_radius)
     if (guard) { if (nfma) TM_FINR_CASE(true, true); else TM_FINR_CASE(true, false); }

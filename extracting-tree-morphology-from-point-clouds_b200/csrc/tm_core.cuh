@@ -70,6 +70,7 @@ struct tm_handle {
     int64_t m = 0;
     bool have_cyl = false;
     tmn::DevBuf recA, recB;          // float4[M]: {start.xyz, axis_length}, {unit.xyz, radius}
+    tmn::DevBuf recAB;               // float4[2M]: the same records interleaved (one 32-byte sector per cylinder: gathers)
     tmn::DevBuf ids;                 // int32[M]
     tmn::DevBuf boxlo, boxhi;        // float4[M]: solid-cylinder AABB (w unused)
     tmn::DevBuf bbox;                // 6 floats as ordered ints: global min/max + counters
@@ -96,7 +97,8 @@ struct tm_handle {
     // ---- per-call scratch ----
     tmn::DevBuf keys;                // u64 per point (brute mode) / per pending slot (grid mode)
     tmn::DevBuf pt_cell, pt_rank;    // uint32 per point
-    tmn::DevBuf cell_count, cell_start, block_sums;
+    tmn::DevBuf cell_count, cell_start, block_sums;      // index build (cell_count / cell_start) and scan partials
+    tmn::DevBuf cells;               // uint2 per voxel: {point count -> scatter cursor, first sorted point}
     tmn::DevBuf sorted_pts;          // float4 per point {x,y,z,bits(original row)}
     tmn::DevBuf items;               // uint4 per work item
     tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)

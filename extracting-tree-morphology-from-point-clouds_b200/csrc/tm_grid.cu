@@ -279,14 +279,14 @@ __device__ __forceinline__ Tri tri_of_count(uint32_t cnt) {
 }
 
 // phase A: per-block totals
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ count, uint32_t ncodes,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ count, int stride, uint32_t ncodes,
                                                                    Tri *__restrict__ block_sums) {
     __shared__ Tri total;
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     Tri v{0, 0, 0};
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < ncodes) v = tri_add(v, tri_of_count(count[base + i]));
+        if (base + i < ncodes) v = tri_add(v, tri_of_count(count[static_cast<size_t>(base + i) * stride]));
     block_exclusive_scan(v, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
@@ -316,11 +316,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(Tri *__restri
 }
 
 // phase C: final offsets.  mode 0 (tile pool): start[code] only (+ the grand total at start[ncodes]).
+// In mode 1 `count` and `start` are the SAME array of {count, start} cells (stride 2): a thread reads the counts of its
+// own cells, then rewrites them as {0, start} — the low word becomes the scatter pass's cursor, so that ONE 64-bit
+// atomicAdd returns both the run start and the slot inside the run.
 // mode 1 (points): start[code] = first sorted point of the voxel, and the voxel's work items
 // {tile offset, near length, first point, point count <= 64 | far length << 8} are emitted in voxel-id order.
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *__restrict__ count, uint32_t ncodes,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *count, int stride, uint32_t ncodes,
                                                                   const Tri *__restrict__ block_sums, int mode,
-                                                                  uint32_t *__restrict__ start,
+                                                                  uint32_t *start,
                                                                   const uint32_t *__restrict__ tile_start,
                                                                   const uint32_t *__restrict__ tile_cnt,
                                                                   const uint32_t *__restrict__ tile_near,
@@ -330,14 +333,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
     Tri v{0, 0, 0};
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        cnt[i] = (base + i < ncodes) ? count[base + i] : 0u;
+        cnt[i] = (base + i < ncodes) ? count[static_cast<size_t>(base + i) * stride] : 0u;
         v = tri_add(v, tri_of_count(cnt[i]));
     }
     Tri run = tri_add(block_exclusive_scan(v, nullptr), block_sums[blockIdx.x]);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         if (base + i < ncodes) {
-            start[base + i] = run.a;
+            if (mode == 0) start[base + i] = run.a;
+            else *reinterpret_cast<uint2 *>(start + 2 * static_cast<size_t>(base + i)) = make_uint2(0u, run.a);
             if (mode == 1 && cnt[i]) {
                 const uint32_t toff = tile_start[base + i], tcnt = tile_cnt[base + i], tnear = tile_near[base + i];
                 const uint32_t far = tcnt - tnear;                       // < 2^24 (tile_sort_kernel)
@@ -357,9 +361,10 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
     Tri *bs = h->block_sums.as<Tri>();
-    scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, ncodes, bs);
+    const int stride = mode == 1 ? 2 : 1;
+    scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);
     scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);
-    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, ncodes, bs, mode, start, tile_start, tile_cnt, tile_near, items);
+    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs, mode, start, tile_start, tile_cnt, tile_near, items);
     TM_CUDA(h, cudaGetLastError());
     return TM_OK;
 }
@@ -513,7 +518,7 @@ __device__ __forceinline__ uint32_t point_code(const GridDev &g, float x, float 
 }
 
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
-                                                        uint32_t *__restrict__ cell_count, int32_t *__restrict__ pend_idx,
+                                                        uint2 *__restrict__ cells, int32_t *__restrict__ pend_idx,
                                                         unsigned long long *__restrict__ pend_keys,
                                                         uint32_t *__restrict__ brute_slots, DevStats *__restrict__ st) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
         const float *p = pts + i * row_stride;
         const uint32_t code = point_code(g, p[0], p[1], p[2]);
         if (code != NO_CELL) {
-            atomicAdd(&cell_count[code], 1u);
+            atomicAdd(&cells[code].x, 1u);
         } else {
             const unsigned int s = atomicAdd(&st->pending, 1u);
             pend_idx[s] = static_cast<int32_t>(i) | OUTSIDE_BIT;
@@ -531,18 +536,18 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
     }
 }
 
-// pass 2: each point takes the next free slot of its voxel's run (the counter runs back down to zero)
+// pass 2: each point takes the next free slot of its voxel's run.  A cell is {cursor, run start}: one 64-bit atomic
+// increments the cursor and returns both words (one L2 request instead of an atomic plus a gather).
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
-                                                          uint32_t *__restrict__ cell_count,
-                                                          const uint32_t *__restrict__ cell_start,
-                                                          float4 *__restrict__ sorted) {
+                                                          uint2 *__restrict__ cells, float4 *__restrict__ sorted) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float *p = pts + i * row_stride;
         const float x = p[0], y = p[1], z = p[2];
         const uint32_t code = point_code(g, x, y, z);
         if (code == NO_CELL) continue;
-        const uint32_t pos = cell_start[code] + atomicSub(&cell_count[code], 1u) - 1u;
+        const unsigned long long cell = atomicAdd(reinterpret_cast<unsigned long long *>(cells + code), 1ull);
+        const uint32_t pos = static_cast<uint32_t>(cell >> 32) + static_cast<uint32_t>(cell);
         sorted[pos] = make_float4(x, y, z, __int_as_float(static_cast<int>(i)));
     }
 }
@@ -1025,8 +1030,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     // scratch
     const size_t max_occ = std::min<size_t>(n, ncodes);
     const size_t max_items = n / PTS_PER_ITEM + max_occ + 1;
-    TM_CUDA(h, h->cell_count.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
-    TM_CUDA(h, h->cell_start.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncodes) + 1)));
+    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
     TM_CUDA(h, h->items.ensure(sizeof(uint4) * max_items));
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
@@ -1037,21 +1041,20 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
-    TM_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, sizeof(uint32_t) * ncodes, st));
+    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * ncodes, st));
 
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
-    bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cell_count.as<uint32_t>(),
+    bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cells.as<uint2>(),
                                                 h->pend_idx.as<int32_t>(), h->keys.as<unsigned long long>(),
                                                 h->brute_slots.as<uint32_t>(), dst);
     TM_KCHECK(h, st, "bin_count_kernel");
     mark(h, 1, st);
-    int rc = run_scan(h, h->cell_count.as<uint32_t>(), ncodes, 1, h->cell_start.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
+    int rc = run_scan(h, h->cells.as<uint32_t>(), ncodes, 1, h->cells.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
                       h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), dst, st);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
     mark(h, 2, st);
-    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cell_count.as<uint32_t>(),
-                                                  h->cell_start.as<uint32_t>(), h->sorted_pts.as<float4>());
+    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cells.as<uint2>(), h->sorted_pts.as<float4>());
     TM_KCHECK(h, st, "bin_scatter_kernel");
 
     mark(h, 3, st);
