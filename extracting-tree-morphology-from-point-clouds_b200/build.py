@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libtreemorph_nn.so")
 SOURCES = ["tm_api.cu", "tm_brute.cu", "tm_grid.cu", "tm_small.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "--threads", "4"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "--threads", "4"]
 
 
 def find_nvcc() -> str | None:

@@ -5,6 +5,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <thread>
+#include <vector>
+
+#include <sched.h>
 
 #include "tm_core.cuh"
 #include "tm_eval.cuh"
@@ -379,6 +383,36 @@ int tm_assemble_records(tm_handle *h, const void *cloud, int32_t dtype, int64_t 
 }
 
 // ---- pipelined host entry -----------------------------------------------------------------------
+// Staging copies between the caller's pageable arrays and the pinned buffers.  A fresh numpy output array is untouched
+// memory: one thread page-faults it at ~7 GB/s, which is slower than the PCIe link, so large copies are split over a
+// few host threads (bounded by the CPUs this process may run on).
+static unsigned host_copy_threads() {
+    static const unsigned n = [] {
+        cpu_set_t set;
+        unsigned avail = 0;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = static_cast<unsigned>(CPU_COUNT(&set));
+        if (avail == 0) avail = std::thread::hardware_concurrency();
+        return std::max(1u, std::min(avail, 8u));
+    }();
+    return n;
+}
+
+static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const unsigned nt = host_copy_threads();
+    if (bytes < (8u << 20) || nt <= 1) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / nt) + 4095) & ~static_cast<size_t>(4095);
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (unsigned t = 1; t < nt; ++t) {
+        const size_t lo = t * per;
+        if (lo >= bytes) break;
+        const size_t len = std::min(per, bytes - lo);
+        pool.emplace_back([=] { memcpy(static_cast<unsigned char *>(dst) + lo, static_cast<const unsigned char *>(src) + lo, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (auto &th : pool) th.join();
+}
+
 static bool host_is_pinned(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -437,7 +471,7 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         TM_CUDA(h, cudaEventSynchronize(h->pipe_event[4 + b]));
         if (!out_pinned) {
             const int64_t cnt = std::min(chunk, n - c * chunk);
-            memcpy(out_records_host + c * chunk * 7, h->pinned_out[b], static_cast<size_t>(cnt) * 7 * sizeof(double));
+            par_memcpy(out_records_host + c * chunk * 7, h->pinned_out[b], static_cast<size_t>(cnt) * 7 * sizeof(double));
             if (out_dist_host)
                 memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b]) + rec_bytes,
                        static_cast<size_t>(cnt) * sizeof(float));
@@ -456,7 +490,7 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
             TM_CUDA(h, cudaStreamWaitEvent(s_in, h->pipe_event[6 + b], 0));
         }
         if (!in_pinned) {
-            memcpy(h->pinned_in[b], csrc, bytes);
+            par_memcpy(h->pinned_in[b], csrc, bytes);
             TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b], bytes, cudaMemcpyHostToDevice, s_in));
         } else {
             TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));

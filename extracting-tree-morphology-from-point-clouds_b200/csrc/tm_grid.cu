@@ -431,7 +431,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     h->grid = d;
     // D_near = nfac * h covers the bulk of a surface-sampled cloud; D_max = dfac * h bounds the far part of the tiles
     // (tuning hooks for experiments; the defaults are the shipped values)
-    float nfac = 1.0f, dfac = 2.0f;
+    float nfac = 0.8f, dfac = 2.0f;
     if (const char *env = getenv("TM_NEAR_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v >= 0.1f && v <= 4.f) nfac = v; }
     if (const char *env = getenv("TM_REACH_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v >= 0.25f && v <= 8.f) dfac = v; }
     if (dfac < nfac) dfac = nfac;
