@@ -111,10 +111,15 @@ def main():
     pts = synth.sample_points(qsm, 5_000_000, seed=4, noise="model")
     df = synth.qsm_dataframe(qsm)
     cloud64 = pts.astype(np.float64)
-    Projection.generate_offset_cloud_cuda_batched(cloud64[:100_000], df, dev)
     t0 = time.perf_counter()
-    rec = Projection.generate_offset_cloud_cuda_batched(cloud64, df, dev)
-    dt = time.perf_counter() - t0
+    rec = Projection.generate_offset_cloud_cuda_batched(cloud64, df, dev)        # first call: allocations, index build
+    cold = time.perf_counter() - t0
+    warm = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rec = Projection.generate_offset_cloud_cuda_batched(cloud64, df, dev)
+        warm.append(time.perf_counter() - t0)
+    dt = float(np.median(warm))
     rng = np.random.default_rng(9)
     sub = rng.choice(len(pts), 20_000, replace=False)
     arrs = synth.cylinder_arrays(qsm, oracle.VARIANT_B.axis_eps)
@@ -123,7 +128,7 @@ def main():
     ok = bool(np.array_equal(rec[sub, 6], ora["id"].astype(np.float64)) and np.array_equal(rec[sub, 3:6], ora["offset"].astype(np.float64), equal_nan=True)
               and np.array_equal(rec[sub, :3], cloud64[sub]))
     res["config4"] = {"points": 5_000_000, "cylinders": 50_000, "api": "Modules.Projection.generate_offset_cloud_cuda_batched (float64 host cloud -> (N,7) float64)",
-                      "seconds": dt, "points_per_s": 5e6 / dt, "vs_oracle_bitwise_rows": 20_000, "vs_oracle_bitwise": ok}
+                      "seconds": dt, "seconds_first_call": cold, "points_per_s": 5e6 / dt, "vs_oracle_bitwise_rows": 20_000, "vs_oracle_bitwise": ok}
     print("config4", json.dumps(res["config4"]), flush=True)
     del rec, cloud64
 

@@ -280,6 +280,35 @@ def test_long_special_and_remote_cylinders(eng, vn):
     assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == len(pts)
 
 
+@pytest.mark.parametrize("vn", ["A", "B"])
+def test_crowded_voxels_and_noise_clouds(eng, vn):
+    """Tiles longer than the in-kernel sort (thousands of twigs in one voxel: unsorted fallback, many staging
+    chunks), a dense cluster of duplicates, and a cloud that is mostly far from every cylinder (far part of the
+    tiles, ball-query ring search with and without an incumbent)."""
+    base = make_case(600, 20_000, seed=61, variant=vn)
+    rng = np.random.default_rng(62)
+    k = 3000
+    centre = np.array([1.1, 0.6, 2.3])
+    p0 = centre + rng.uniform(-0.1, 0.1, (k, 3))
+    d = rng.normal(size=(k, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rows = [[*p0[i], *d[i], rng.uniform(0.005, 0.04), rng.uniform(0.001, 0.004)] for i in range(k)]
+    rows += [[*centre, 0.0, 0.6, 0.8, 0.05, 0.002]] * 40                                   # 40 identical twigs: lowest row wins
+    case = _append_cylinders(base, rows)
+    near = (centre + rng.normal(0, 0.08, (30_000, 3))).astype(np.float32)
+    haze = (rng.uniform(-1, 1, (40_000, 3)) * [6, 6, 6] + [0, 0, 6]).astype(np.float32)      # 0 .. several metres from the tree
+    pts = np.concatenate([case["points"], near, haze])
+    ora = oracle_label(case, pts)
+    _install(eng, case)
+    for mode in ("grid", "brute"):
+        got = _label(eng, case, pts, mode)
+        assert_parity(got, ora, f"crowded/{vn}/{mode}", require_bitwise=True)
+        if mode == "grid":
+            st = eng.stats()
+            assert st["points_far"] > 0 and st["points_ring"] > 0
+            assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == len(pts)
+
+
 # ---- full-size properties ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,m", [(1_000_000, 10_000), (10_000_000, 50_000)])
