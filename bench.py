@@ -37,7 +37,7 @@ OPS_PER_PAIR = 81                 # fp32 lane-ops per evaluated pair in referenc
 BYTES_PER_POINT = 36              # compulsory HBM traffic per point: 12 B xyz in + 24 B index/id/dist/offset out
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-call kernel, from the committed ncu --set full capture
 # of THIS command at the default workload (profiles/r01e_grid_kernels.md); null for any other workload
-NCU_DRAM_BYTES = {"evaluate": 345.46e6, "bin": 127.13e6, "scatter": 276.80e6, "epilogue": 316.56e6, "ring": 7.93e6}
+NCU_DRAM_BYTES = {"evaluate": 345.46e6, "bin": 127.13e6, "scatter": 276.80e6, "epilogue": 316.56e6, "tree": 7.93e6}
 
 
 def load_peaks():
@@ -349,7 +349,7 @@ def main():
     # ---- rooflines
     hbm_peak, peak_kind = load_peaks()
     fp32_peak = eng.fp32_peak()
-    dom = max(("evaluate", "ring", "exhaustive", "pending", "bin", "scatter", "scan", "epilogue"), key=lambda k: phases.get(k, 0.0))
+    dom = max(("evaluate", "tree", "exhaustive", "pending", "bin", "scatter", "scan", "epilogue"), key=lambda k: phases.get(k, 0.0))
     dom_ms = phases.get(dom, 0.0) or ms_per_step
     achieved_gbs = BYTES_PER_POINT * N_POINTS / (dom_ms * 1e-3) / 1e9
     pairs = stats["pairs_evaluated"]
@@ -391,7 +391,7 @@ def main():
                "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {host_threads()} threads "
                          f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
 
-    launches_per_step = {"grid": 10, "auto": 10, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, ring, exhaustive, pending winners, epilogue
+    launches_per_step = {"grid": 10, "auto": 10, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, tree search, exhaustive, pending winners, epilogue
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -13,9 +13,9 @@ from . import build as _build
 TM_OK, TM_ERR_INVALID, TM_ERR_NO_CYLINDERS, TM_ERR_CUDA, TM_ERR_NOMEM, TM_ERR_STATE = range(6)
 TM_MODE_AUTO, TM_MODE_BRUTE, TM_MODE_GRID = 0, 1, 2
 TM_F32, TM_F64 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 TM_PHASES = 9
-PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "ring", "exhaustive", "pending", "epilogue", "total")
+PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "tree", "exhaustive", "pending", "epilogue", "total")
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
 
@@ -27,7 +27,7 @@ class TmParams(ctypes.Structure):
 
 class TmStats(ctypes.Structure):
     _fields_ = [("pairs_evaluated", ctypes.c_uint64), ("cull_tests", ctypes.c_uint64),
-                ("points_grid", ctypes.c_uint64), ("points_far", ctypes.c_uint64), ("points_ring", ctypes.c_uint64),
+                ("points_grid", ctypes.c_uint64), ("points_far", ctypes.c_uint64), ("points_ring", ctypes.c_uint64), ("points_tree", ctypes.c_uint64),
                 ("points_brute", ctypes.c_uint64), ("index_entries", ctypes.c_uint64),
                 ("voxels_occupied", ctypes.c_uint32), ("work_items", ctypes.c_uint32),
                 ("mode_used", ctypes.c_uint32), ("cell_size", c_f32), ("reach", c_f32), ("near_reach", c_f32),

@@ -245,10 +245,10 @@ int tm_destroy(tm_handle *h) {
     if (!h) return TM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->recAB, &h->cells, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
+    tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->recAB, &h->cells, &h->bvh_nodes, &h->bvh_rows, &h->bvh_leafAB, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->pt_cell, &h->pt_rank, &h->cell_count,
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
-                          &h->pend_idx, &h->brute_slots, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
+                          &h->pend_idx, &h->brute_slots, &h->pend_done, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
                           &h->small_out};
     for (auto *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
@@ -659,7 +659,8 @@ int tm_get_stats(tm_handle *h, tm_stats *out) {
         s.cull_tests += d.cull_tests;
         s.points_grid += static_cast<uint64_t>(h->last_n) - d.pending - d.far_certified;
         s.points_far += d.far_certified;
-        s.points_ring += d.pending - d.n_brute;
+        s.points_ring += d.ring_certified;
+        s.points_tree += d.pending - d.n_brute - d.ring_certified;
         s.points_brute += d.n_brute;
         s.index_entries = h->index_entries;
         s.voxels_occupied = d.voxels_occupied;

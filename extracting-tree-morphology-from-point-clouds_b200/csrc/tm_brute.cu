@@ -142,8 +142,8 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
     }
 }
 
-// Exhaustive search for the SHORT list of pending points the voxel tiles and the ring search could not certify
-// (outside the grid, non-finite, farther than RING_MAX shells from every cylinder; the count lives on the device).
+// Exhaustive search for the SHORT list of pending points nothing can bound (non-finite coordinates; the count lives on
+// the device).
 // One warp per (point, 1024-cylinder chunk) task: the lanes stride over the chunk's records straight from global
 // memory (coalesced 512-byte requests, the table is L2 resident), skip candidates whose capsule lies beyond the
 // incumbent (same cull as the tile kernel, with a per-point rounding allowance), keep a 64-bit (distance, index)
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) brute_cull_kernel(BruteCullArgs a) {
         const float px = p[0], py = p[1], pz = p[2];
         // rounding allowance at this point's own coordinate scale (inf / NaN coordinates: nothing is culled)
         const float slack = 1e-4f + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
-        const unsigned long long key0 = a.keys[slot];          // incumbent from the ring search / other chunks (may be stale)
+        const unsigned long long key0 = a.keys[slot];          // incumbent from the other chunks (may be stale)
         unsigned long long best = KEY_NONE;
         float thr = thr_of(key0, slack);
         if (!(fabsf(px) + fabsf(py) + fabsf(pz) < 3.0e38f)) thr = __int_as_float(0x7fc00000);
@@ -311,7 +311,7 @@ int label_brute(tm_handle *h, const LabelArgs &a) {
     return TM_OK;
 }
 
-// winning rows of the pending slots (ring-certified and exhaustive alike) -> win[original row]
+// winning rows of the pending slots (tree search and exhaustive alike) -> win[original row]
 __global__ void __launch_bounds__(256) pending_winner_kernel(const int32_t *__restrict__ pend_idx, const unsigned int *__restrict__ d_count,
                                                              const unsigned long long *__restrict__ keys, int32_t *__restrict__ win) {
     const unsigned int n = *d_count;

@@ -1,0 +1,299 @@
+// Bounding-volume hierarchy over the cylinders' capsule boxes: the search structure for the points the voxel tiles
+// cannot certify (clutter, foliage, ground: anything farther than D_max from every cylinder, or outside the grid).
+//
+// The tiles answer a surface-sampled point with ~17 culls; a point d metres away from the tree would have to look at
+// every cylinder within d of its voxel — thousands in a crown — whereas a per-point tree descent with the incumbent as
+// the pruning radius visits O(log M) boxes plus the few leaves that are nearly as close as the winner.
+//
+//   build (per table, host):  Morton-order the regular cylinders by box centre, median-split the order recursively,
+//                             leaves of <= 4 cylinders, node = the two child boxes + child codes in one 64-byte record.
+//   search (per call):        one THREAD per pending point, explicit stack in local memory, nearer child first, node
+//                             pruned when dist(p, box) > thr(incumbent); leaf cylinders go through the same capsule cull
+//                             and the reference-order evaluation as everywhere else.  The incumbent left by the tile
+//                             kernel seeds the search.
+//
+// Exactness: capsule(c) lies inside box(c) (padded, tm_api.cu pack_kernel) and box(c) inside every ancestor's box, so
+// dist_ref(p,c) >= dist(p, capsule(c)) >= dist(p, box(node)): a pruned subtree cannot beat or tie the incumbent.  The
+// search is exhaustive up to pruning, so every point it handles is final.  Cylinders that cannot be bounded (special)
+// and variant A's axis-parallel ones are not in the tree: the tile kernel has already evaluated them for the points it
+// saw; for points outside the grid they are evaluated here.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "tm_core.cuh"
+#include "tm_eval.cuh"
+
+namespace tmn {
+
+constexpr int BVH_LEAF = 4;
+constexpr int BVH_STACK = 40;
+
+struct __align__(16) BvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int32_t c0, c1;          // >= 0: internal node; < 0: leaf, -1 - ((first << 3) | (count - 1))
+    int32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "one node = two 32-byte sectors");
+
+// ---- host build ------------------------------------------------------------------------------------------------
+static inline uint32_t expand10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+struct BuildCtx {
+    const std::vector<float4> *lo, *hi;
+    const std::vector<int32_t> *order;
+    std::vector<BvhNode> nodes;
+};
+
+static void box_of(const BuildCtx &cx, int first, int count, float *lo, float *hi) {
+    for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+    for (int i = first; i < first + count; ++i) {
+        const float4 a = (*cx.lo)[(*cx.order)[i]], b = (*cx.hi)[(*cx.order)[i]];
+        lo[0] = std::min(lo[0], a.x); lo[1] = std::min(lo[1], a.y); lo[2] = std::min(lo[2], a.z);
+        hi[0] = std::max(hi[0], b.x); hi[1] = std::max(hi[1], b.y); hi[2] = std::max(hi[2], b.z);
+    }
+}
+
+// returns the child code of the subtree over order[first, first + count) and its box
+static int32_t build_range(BuildCtx &cx, int first, int count, float *lo, float *hi) {
+    if (count <= BVH_LEAF) {
+        box_of(cx, first, count, lo, hi);
+        return -1 - ((first << 3) | (count - 1));
+    }
+    const int id = static_cast<int>(cx.nodes.size());
+    cx.nodes.emplace_back();
+    const int half = count / 2;
+    float l0[3], h0[3], l1[3], h1[3];
+    const int32_t c0 = build_range(cx, first, half, l0, h0);
+    const int32_t c1 = build_range(cx, first + half, count - half, l1, h1);
+    BvhNode &n = cx.nodes[id];
+    for (int k = 0; k < 3; ++k) {
+        n.lo0[k] = l0[k]; n.hi0[k] = h0[k]; n.lo1[k] = l1[k]; n.hi1[k] = h1[k];
+        lo[k] = std::min(l0[k], l1[k]);
+        hi[k] = std::max(h0[k], h1[k]);
+    }
+    n.c0 = c0; n.c1 = c1; n.pad[0] = n.pad[1] = 0;
+    return id;
+}
+
+__global__ void bvh_leaf_gather_kernel(const int32_t *__restrict__ rows, int n, const float4 *__restrict__ recAB,
+                                       float4 *__restrict__ leafAB) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = rows[i];
+    leafAB[2 * i] = recAB[2 * r];
+    leafAB[2 * i + 1] = recAB[2 * r + 1];
+}
+
+int build_bvh(tm_handle *h, cudaStream_t stream) {
+    const int m = static_cast<int>(h->m);
+    h->bvh_count = 0;
+    h->bvh_root = 0;
+    if (m > (1 << 27)) return fail(h, TM_ERR_INVALID, "tm_set_cylinders: more than 2^27 cylinders%s%s");
+    std::vector<float4> lo(m), hi(m);
+    TM_CUDA(h, cudaMemcpyAsync(lo.data(), h->boxlo.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
+    TM_CUDA(h, cudaMemcpyAsync(hi.data(), h->boxhi.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
+    TM_CUDA(h, cudaStreamSynchronize(stream));
+    std::vector<int32_t> order;
+    order.reserve(m);
+    float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int c = 0; c < m; ++c) {
+        if (!(lo[c].w == 0.f)) continue;                  // special cylinders are not in the tree
+        order.push_back(c);
+        const float cx = 0.5f * (lo[c].x + hi[c].x), cy = 0.5f * (lo[c].y + hi[c].y), cz = 0.5f * (lo[c].z + hi[c].z);
+        clo[0] = std::min(clo[0], cx); clo[1] = std::min(clo[1], cy); clo[2] = std::min(clo[2], cz);
+        chi[0] = std::max(chi[0], cx); chi[1] = std::max(chi[1], cy); chi[2] = std::max(chi[2], cz);
+    }
+    const int n = static_cast<int>(order.size());
+    if (n == 0) return TM_OK;
+    std::vector<uint64_t> keyed(n);
+    float scale[3];
+    for (int k = 0; k < 3; ++k) scale[k] = chi[k] > clo[k] ? 1023.999f / (chi[k] - clo[k]) : 0.f;
+    for (int i = 0; i < n; ++i) {
+        const int c = order[i];
+        const uint32_t qx = static_cast<uint32_t>((0.5f * (lo[c].x + hi[c].x) - clo[0]) * scale[0]);
+        const uint32_t qy = static_cast<uint32_t>((0.5f * (lo[c].y + hi[c].y) - clo[1]) * scale[1]);
+        const uint32_t qz = static_cast<uint32_t>((0.5f * (lo[c].z + hi[c].z) - clo[2]) * scale[2]);
+        const uint32_t code = expand10(qx) | (expand10(qy) << 1) | (expand10(qz) << 2);
+        keyed[i] = (static_cast<uint64_t>(code) << 32) | static_cast<uint32_t>(c);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (int i = 0; i < n; ++i) order[i] = static_cast<int32_t>(static_cast<uint32_t>(keyed[i]));
+    BuildCtx cx;
+    cx.lo = &lo; cx.hi = &hi; cx.order = &order;
+    cx.nodes.reserve(static_cast<size_t>(n) / 2 + 2);
+    float rlo[3], rhi[3];
+    h->bvh_root = build_range(cx, 0, n, rlo, rhi);
+    h->bvh_count = n;
+    const size_t nnodes = std::max<size_t>(cx.nodes.size(), 1);
+    TM_CUDA(h, h->bvh_nodes.ensure(sizeof(BvhNode) * nnodes));
+    TM_CUDA(h, h->bvh_rows.ensure(sizeof(int32_t) * n));
+    TM_CUDA(h, h->bvh_leafAB.ensure(sizeof(float4) * 2 * n));
+    if (!cx.nodes.empty())
+        TM_CUDA(h, cudaMemcpyAsync(h->bvh_nodes.p, cx.nodes.data(), sizeof(BvhNode) * cx.nodes.size(), cudaMemcpyHostToDevice, stream));
+    TM_CUDA(h, cudaMemcpyAsync(h->bvh_rows.p, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+    bvh_leaf_gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(h->bvh_rows.as<int32_t>(), n, h->recAB.as<float4>(),
+                                                              h->bvh_leafAB.as<float4>());
+    TM_KCHECK(h, stream, "bvh_leaf_gather_kernel");
+    TM_CUDA(h, cudaStreamSynchronize(stream));            // the host vectors go out of scope
+    return TM_OK;
+}
+
+// ---- search ------------------------------------------------------------------------------------------------------
+struct BvhArgs {
+    const float *pts;
+    int64_t row_stride;
+    const int32_t *pend_idx;
+    unsigned long long *pend_keys;
+    const unsigned int *d_pending;
+    const uint8_t *pend_done;      // slots the ring search has already certified
+    const BvhNode *nodes;
+    const float4 *leafAB;
+    const int32_t *leaf_rows;
+    int32_t root;
+    int32_t count;
+    const float4 *recA, *recB;
+    const int32_t *special, *aligned;
+    uint32_t n_special, n_aligned;
+    float atol, eps, maxabs;
+    DevStats *st;
+};
+
+__device__ __forceinline__ float box_dist2(float px, float py, float pz, const float *lo, const float *hi) {
+    const float gx = fmaxf(fmaxf(lo[0] - px, px - hi[0]), 0.f);
+    const float gy = fmaxf(fmaxf(lo[1] - py, py - hi[1]), 0.f);
+    const float gz = fmaxf(fmaxf(lo[2] - pz, pz - hi[2]), 0.f);
+    return fmaf(gz, gz, fmaf(gy, gy, gx * gx));
+}
+
+template <bool GUARD, bool NFMA>
+__global__ void __launch_bounds__(128) bvh_kernel(BvhArgs a) {
+    const unsigned int n_pend = *a.d_pending;
+    const int lane = threadIdx.x & 31;
+    unsigned long long pairs = 0, culls = 0;
+    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_pend; slot += gridDim.x * blockDim.x) {
+        if (a.pend_done[slot]) continue;
+        const int32_t ri = a.pend_idx[slot];
+        const float *p = a.pts + static_cast<int64_t>(ri & 0x7fffffff) * a.row_stride;
+        const float px = p[0], py = p[1], pz = p[2];
+        if (!(fabsf(px) + fabsf(py) + fabsf(pz) < 3.0e38f)) continue;      // non-finite: the exhaustive kernel's
+        unsigned long long key = a.pend_keys[slot];
+        if (static_cast<uint32_t>(key >> 32) == 0u) continue;              // NaN incumbent is final
+        const float slack = 1e-4f + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
+        if (ri < 0) {
+            // outside the grid: the tile kernel never saw this point
+            for (uint32_t e = 0; e < a.n_special; ++e) {
+                const uint32_t j = static_cast<uint32_t>(a.special[e]);
+                const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(px, py, pz, a.recA[j], a.recB[j], a.atol, a.eps, nullptr), j);
+                key = k < key ? k : key;
+                ++pairs;
+            }
+            if (!GUARD) {
+                for (uint32_t e = 0; e < a.n_aligned; ++e) {
+                    const uint32_t j = static_cast<uint32_t>(a.aligned[e]);
+                    const float4 ca = a.recA[j], cb = a.recB[j];
+                    if (on_axis_line(px, py, pz, ca, cb)) {
+                        const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr), j);
+                        key = k < key ? k : key;
+                        ++pairs;
+                    }
+                }
+            }
+        }
+        if (a.count > 0 && static_cast<uint32_t>(key >> 32) != 0u) {
+            float thr = thr_of(key, slack);                     // NaN while there is no incumbent: nothing is pruned
+            int32_t stk_node[BVH_STACK];
+            float stk_d2[BVH_STACK];
+            int sp = 0;
+            int32_t node = a.root;
+            for (;;) {
+                if (node < 0) {
+                    const int32_t code = -1 - node;
+                    const int first = code >> 3, cnt = (code & 7) + 1;
+                    for (int k = 0; k < cnt; ++k) {
+                        const float4 ca = a.leafAB[2 * (first + k)], cb = a.leafAB[2 * (first + k) + 1];
+                        ++culls;
+                        if (cull_pass(px, py, pz, ca, cb, thr)) {
+                            const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr);
+                            const unsigned long long kk = make_key(d, static_cast<uint32_t>(a.leaf_rows[first + k]));
+                            ++pairs;
+                            if (kk < key) { key = kk; thr = thr_of(key, slack); }
+                        }
+                    }
+                    if (static_cast<uint32_t>(key >> 32) == 0u) break;   // NaN: nothing can beat it
+                    node = 0x7fffffff;                                    // pop
+                } else {
+                    const float4 *q = reinterpret_cast<const float4 *>(a.nodes + node);
+                    const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                    const float lo0[3] = {q0.x, q0.y, q0.z}, hi0[3] = {q0.w, q1.x, q1.y};
+                    const float lo1[3] = {q1.z, q1.w, q2.x}, hi1[3] = {q2.y, q2.z, q2.w};
+                    const int32_t c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+                    const float d0 = box_dist2(px, py, pz, lo0, hi0), d1 = box_dist2(px, py, pz, lo1, hi1);
+                    const float t2 = thr * thr;
+                    const bool h0 = !(d0 > t2), h1 = !(d1 > t2);
+                    if (h0 && h1) {
+                        const bool first0 = d0 <= d1;
+                        if (sp < BVH_STACK) { stk_node[sp] = first0 ? c1 : c0; stk_d2[sp] = first0 ? d1 : d0; ++sp; }
+                        node = first0 ? c0 : c1;
+                        continue;
+                    }
+                    if (h0) { node = c0; continue; }
+                    if (h1) { node = c1; continue; }
+                    node = 0x7fffffff;
+                }
+                // pop the next subtree that can still hold a winner
+                bool found = false;
+                while (sp > 0) {
+                    --sp;
+                    if (!(stk_d2[sp] > thr * thr)) { node = stk_node[sp]; found = true; break; }
+                }
+                if (!found) break;
+            }
+        }
+        a.pend_keys[slot] = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+        culls += __shfl_xor_sync(0xffffffffu, culls, o);
+    }
+    if (lane == 0 && (pairs | culls)) {
+        atomicAdd(&a.st->pairs_ring, pairs);
+        atomicAdd(&a.st->cull_tests, culls);
+    }
+}
+
+int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst) {
+    BvhArgs b;
+    b.pts = a.pts; b.row_stride = a.row_stride;
+    b.pend_idx = h->pend_idx.as<int32_t>();
+    b.pend_keys = h->keys.as<unsigned long long>();
+    b.d_pending = &dst->pending;
+    b.pend_done = h->pend_done.as<uint8_t>();
+    b.nodes = h->bvh_nodes.as<BvhNode>();
+    b.leafAB = h->bvh_leafAB.as<float4>();
+    b.leaf_rows = h->bvh_rows.as<int32_t>();
+    b.root = h->bvh_root; b.count = h->bvh_count;
+    b.recA = h->recA.as<float4>(); b.recB = h->recB.as<float4>();
+    b.special = h->special.as<int32_t>(); b.aligned = h->aligned.as<int32_t>();
+    b.n_special = h->n_special; b.n_aligned = h->n_aligned;
+    b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = h->maxabs;
+    b.st = dst;
+    const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
+    const int grid = h->sm_count * 16;
+    if (guard) { if (nfma) bvh_kernel<true, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<true, false><<<grid, 128, 0, a.stream>>>(b); }
+    else       { if (nfma) bvh_kernel<false, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<false, false><<<grid, 128, 0, a.stream>>>(b); }
+    TM_KCHECK(h, a.stream, "bvh_kernel");
+    return TM_OK;
+}
+
+}  // namespace tmn

@@ -48,7 +48,7 @@ struct GridDesc {
 // device-side counters of one labelling call (mirrors tm_stats where it is data dependent)
 struct DevStats {
     unsigned long long pairs_grid;   // full evaluations in the voxel-tile kernel
-    unsigned long long pairs_ring;   // full evaluations in the ring-search and exhaustive-with-cull kernels
+    unsigned long long pairs_ring;   // full evaluations in the tree-search and exhaustive-with-cull kernels
     unsigned long long cull_tests;   // capsule lower-bound tests, all kernels
     unsigned long long points_binned;
     unsigned int voxels_occupied;
@@ -56,6 +56,7 @@ struct DevStats {
     unsigned int pending;            // points the voxel-tile kernel could not certify (slots of pend_idx / keys)
     unsigned int n_brute;            // of those, points that need the exhaustive kernel (slots of brute_slots)
     unsigned int far_certified;      // points certified by the far part of their own tile (inside the tile kernel)
+    unsigned int ring_certified;     // points certified by the ring search
     unsigned int pad[1];
 };
 
@@ -92,6 +93,10 @@ struct tm_handle {
     tmn::DevBuf special;             // int32[]: non-finite / non-unit cylinders, evaluated for every point
     tmn::DevBuf aligned;             // int32[]: axis-parallel cylinders (variant A: NaN for points on their axis LINE)
     uint32_t n_long = 0, n_special = 0, n_listed = 0, n_aligned = 0;
+    tmn::DevBuf bvh_nodes;           // 64-byte nodes of the bounding-volume hierarchy over the regular cylinders
+    tmn::DevBuf bvh_rows;            // int32: cylinder row per leaf slot (Morton order)
+    tmn::DevBuf bvh_leafAB;          // float4[2 x count]: records in leaf order
+    int32_t bvh_root = 0, bvh_count = 0;
     uint64_t index_entries = 0;
 
     // ---- per-call scratch ----
@@ -103,6 +108,7 @@ struct tm_handle {
     tmn::DevBuf items;               // uint4 per work item
     tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)
     tmn::DevBuf brute_slots;         // uint32 pending slots that need the exhaustive kernel
+    tmn::DevBuf pend_done;           // uint8 per pending slot: 1 = final after the ring search
     tmn::DevBuf win;                 // int32 per point: winning cylinder row (when the caller passes no out_index)
     tmn::DevBuf dstats;              // tmn::DevStats + cursors
     tmn::DevBuf scratch_f;           // misc float scratch
@@ -184,7 +190,7 @@ struct LabelArgs {
 
 // tm_brute.cu
 int label_brute(tm_handle *h, const LabelArgs &a);
-// grid mode, after the voxel-tile and ring kernels: exhaustive search (with the capsule cull) for the pending
+// grid mode, after the voxel-tile and tree-search kernels: exhaustive search (with the capsule cull) for the pending
 // slots listed in h->brute_slots, then the winning row of EVERY pending slot goes to win[original row]
 int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win, float maxabs);
 // streaming winner-only epilogue over all rows: win[row] -> index / id / distance / offset / radius
@@ -203,6 +209,9 @@ struct SmallArgs {
     int32_t *index;
 };
 int run_proximity(tm_handle *h, const SmallArgs &a, bool guard, bool nfma, cudaStream_t st);
+// tm_bvh.cu
+int build_bvh(tm_handle *h, cudaStream_t stream);
+int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst);
 // tm_grid.cu
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream);
 int label_grid(tm_handle *h, const LabelArgs &a);

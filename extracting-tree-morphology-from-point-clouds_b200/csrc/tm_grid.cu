@@ -18,8 +18,11 @@
 //                point's original row (4 bytes, L2 resident).
 //                The few points that are not certified (noise tail) then walk the FAR part of the tile, lanes across
 //                entries in ascending lb order, and stop at the first entry whose lb exceeds their incumbent.
-//     ring:      points still uncertified at D_max search the tiles of the surrounding voxel shells, one CTA per point.
-//     brute:     points outside the grid / not certified within RING_MAX shells: exhaustive search with the same cull.
+//     ring:      a handful of points still uncertified at D_max (noise tail): ball query over the neighbouring voxels'
+//                tiles, one CTA per point (latency-optimised).
+//     tree:      MANY such points (clutter far from every cylinder) and points outside the grid descend the
+//                bounding-volume hierarchy of the cylinders (tm_bvh.cu), one thread per point (throughput-optimised).
+//     brute:     non-finite points: exhaustive search (nothing bounds them).
 //     epilogue:  streaming pass over the rows in input order: recompute the winning pair with full geometry, move to the
 //                mantle, gather the ID, write label + offset (coalesced reads and writes).
 //
@@ -497,6 +500,8 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_KCHECK(h, stream, "tile_sort_kernel");
     TM_CUDA(h, cudaStreamSynchronize(stream));
     h->tile_keys.release();                 // build-time only
+    rc = build_bvh(h, stream);
+    if (rc != TM_OK) return rc;
     h->have_grid = true;
     return TM_OK;
 }
@@ -524,14 +529,17 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float *p = pts + i * row_stride;
-        const uint32_t code = point_code(g, p[0], p[1], p[2]);
+        const float x = p[0], y = p[1], z = p[2];
+        const uint32_t code = point_code(g, x, y, z);
         if (code != NO_CELL) {
             atomicAdd(&cells[code].x, 1u);
         } else {
+            // outside the grid: straight to the tree search; non-finite coordinates cannot be bounded at all and take the
+            // exhaustive kernel
             const unsigned int s = atomicAdd(&st->pending, 1u);
             pend_idx[s] = static_cast<int32_t>(i) | OUTSIDE_BIT;
             pend_keys[s] = KEY_NONE;
-            brute_slots[atomicAdd(&st->n_brute, 1u)] = s;
+            if (!(fabsf(x) + fabsf(y) + fabsf(z) < 3.0e38f)) brute_slots[atomicAdd(&st->n_brute, 1u)] = s;
         }
     }
 }
@@ -811,7 +819,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) 
 
         // ---- certified points: the winning row goes to the point's ORIGINAL row (a 4-byte scatter into an array that
         //      stays L2 resident); the streaming epilogue kernel turns rows into labels + offsets with coalesced
-        //      reads and writes.  The rest join the pending list (ring search) with their incumbent ----
+        //      reads and writes.  The rest join the pending list (tree search) with their incumbent ----
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const bool valid = k ? v1 : v0;
@@ -846,9 +854,12 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// ring search: one CTA per pending point, shells of voxels around its home voxel
+// ring search: one CTA per pending point, shells of voxels around its home voxel.  Latency-optimised: it is the
+// fast answer when only a handful of points (noise tail) are left; with many uncertified points (clutter) it steps
+// aside and the throughput-optimised tree search (tm_bvh.cu) takes all of them.
 // ------------------------------------------------------------------------------------------------
 constexpr int RING_MAX = 8;
+constexpr unsigned int RING_LIMIT = 32768;     // pending points beyond which the tree search is faster (measured crossover ~50k)
 constexpr int RING_WARPS = 8;
 
 struct RingArgs {
@@ -856,7 +867,7 @@ struct RingArgs {
     int64_t row_stride;
     const int32_t *pend_idx;
     unsigned long long *pend_keys;
-    uint32_t *brute_slots;
+    uint8_t *pend_done;            // 1 = this slot is final (the tree search skips it)
     const uint32_t *tile_start, *tile_cnt;
     const float4 *tileA, *tileB;
     const int32_t *tileI;
@@ -894,6 +905,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
     __shared__ uint32_t s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_pend = a.st->pending;
+    if (n_pend > RING_LIMIT) return;
     unsigned long long pairs = 0, culls = 0;
     for (unsigned int task = blockIdx.x; task < n_pend; task += gridDim.x) {
         const int32_t ri = a.pend_idx[task];
@@ -992,8 +1004,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
             __syncthreads();
         }
         if (tid == 0) {
-            a.pend_keys[task] = key;
-            if (!certified) a.brute_slots[atomicAdd(&a.st->n_brute, 1u)] = task;
+            a.pend_keys[task] = key;                 // certified or not, the incumbent seeds whatever comes next
+            if (certified) { a.pend_done[task] = 1; atomicAdd(&a.st->ring_certified, 1u); }
         }
     }
 #pragma unroll
@@ -1038,6 +1050,8 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * n));
     if (!a.out_index) TM_CUDA(h, h->win.ensure(sizeof(int32_t) * n));
     TM_CUDA(h, h->dstats.ensure(sizeof(DevStats) + 64));
+    TM_CUDA(h, h->pend_done.ensure(n));
+    TM_CUDA(h, cudaMemsetAsync(h->pend_done.p, 0, n, st));
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
@@ -1090,13 +1104,14 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
 #undef TM_EVAL_CASE
     TM_KCHECK(h, st, "evaluate_kernel");
 
-    // still uncertified at D_max (beyond the far part of their own tile): shells of neighbouring voxels, one CTA per point
+    // still uncertified at D_max (beyond the far part of their own tile): a handful of points -> ring search, one CTA per
+    // point; many (clutter), or outside the grid -> per-point descent of the bounding-volume hierarchy
     mark(h, 4, st);
     RingArgs rg;
     rg.pts = a.pts; rg.row_stride = a.row_stride;
     rg.pend_idx = h->pend_idx.as<int32_t>();
     rg.pend_keys = h->keys.as<unsigned long long>();
-    rg.brute_slots = h->brute_slots.as<uint32_t>();
+    rg.pend_done = h->pend_done.as<uint8_t>();
     rg.tile_start = h->cyl_cell_start.as<uint32_t>(); rg.tile_cnt = h->cyl_cell_cnt.as<uint32_t>();
     rg.tileA = h->tileA.as<float4>(); rg.tileB = h->tileB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
     rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
@@ -1105,8 +1120,10 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
+    rc = search_bvh(h, a, dst);
+    if (rc != TM_OK) return rc;
 
-    // exhaustive search for what is left, then the epilogue of every pending point
+    // exhaustive search for non-finite points, then the winning rows of every pending point
     mark(h, 5, st);
     rc = finish_pending(h, a, dst, win, h->maxabs);
     if (rc != TM_OK) return rc;

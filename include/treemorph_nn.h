@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TM_ABI_VERSION 3
+#define TM_ABI_VERSION 4
 
 /* status codes */
 #define TM_OK               0
@@ -82,8 +82,9 @@ typedef struct tm_stats {
     uint64_t cull_tests;        /* capsule lower-bound tests that decided whether a pair is evaluated        */
     uint64_t points_grid;       /* points certified by the near part of their own voxel's tile               */
     uint64_t points_far;        /* points certified by the far part of their own voxel's tile                */
-    uint64_t points_ring;       /* points certified by the search of neighbouring voxel shells               */
-    uint64_t points_brute;      /* points answered by the exhaustive kernel (outliers, brute mode)           */
+    uint64_t points_ring;       /* points certified by the ball query over neighbouring voxels (few stragglers) */
+    uint64_t points_tree;       /* points answered by the bounding-volume-hierarchy search (clutter, outside the grid) */
+    uint64_t points_brute;      /* points answered by the exhaustive kernel (non-finite points, brute mode)  */
     uint64_t index_entries;     /* (voxel, cylinder) entries of the static voxel index                       */
     uint32_t voxels_occupied;   /* voxels holding at least one point                                         */
     uint32_t work_items;        /* (voxel, <=64-point slice) items processed by the tile kernel              */
@@ -189,7 +190,7 @@ int tm_get_stats(tm_handle *h, tm_stats *out);
  * Per-phase device timing of tm_label_points (CUDA events recorded on the caller's stream between the
  * phases; off by default).  tm_get_phase_ms synchronises and fills out[0..TM_PHASES):
  *   [0] bin points into voxels   [1] voxel scan + work items   [2] scatter into voxel order
- *   [3] tile kernel: cull + dense evaluation, winning row -> original row   [4] ring search of uncertified points
+ *   [3] tile kernel: cull + dense evaluation, winning row -> original row   [4] ring / tree search of uncertified points
  *   [5] exhaustive kernel (brute mode, or the grid's outliers)   [6] winning rows of the pending points (brute mode: the
  *   winner epilogue)   [7] streaming winner epilogue: rows -> label + offset arrays   [8] whole call
  * Phases that did not run report 0.

@@ -139,7 +139,7 @@ def test_cell_sizes_do_not_change_results(eng):
             assert_same_bits(got[k], ref[k], f"cell {cell}: {k}")
 
 
-def test_far_and_nonfinite_points_take_the_exhaustive_path(eng):
+def test_far_and_nonfinite_points(eng):
     """Points outside the voxel grid, NaN / Inf coordinates: same answers as the oracle (A.4)."""
     case = make_case(1500, 20_000, seed=31, variant="B")
     pts = case["points"].copy()
@@ -154,7 +154,9 @@ def test_far_and_nonfinite_points_take_the_exhaustive_path(eng):
         for mode in ("grid", "brute"):
             got = _label(eng, case, pts, mode)
             assert_parity(got, ora, f"outliers/{mode}", require_bitwise=True)
-    assert eng.stats()["points_brute"] >= 303
+            if mode == "grid":
+                st = eng.stats()
+                assert st["points_brute"] == 2 and st["points_tree"] >= 250       # NaN / Inf rows: exhaustive; the rest: tree
 
 
 def test_empty_and_error_cases(eng):
@@ -249,7 +251,7 @@ def test_axis_parallel_cylinders_far_away(eng, vn):
 def test_long_special_and_remote_cylinders(eng, vn):
     """Cylinders the voxel index cannot list the usual way: one spanning > 32k voxels (long list), one with a
     non-unit axis and one with NaN entries (special list: evaluated for every point), plus points that sit in
-    voxels with empty tiles (ring search) and far outside the grid (exhaustive kernel with the cull)."""
+    voxels with empty tiles and far outside the grid (both: tree search)."""
     base = make_case(2500, 40_000, seed=81, variant=vn)
     d = np.array([1.0, 1.0, 1.0], np.float32) / np.sqrt(np.float32(3))
     rows = [[-6.0, -6.0, 0.0, d[0], d[1], d[2], 20.8, 0.05],                # 20.8 m diagonal: long list
@@ -276,15 +278,16 @@ def test_long_special_and_remote_cylinders(eng, vn):
     with np.errstate(all="ignore"):
         got2 = _label(eng, case2, pts[:20_000], "grid")
         assert_parity(got2, ora2, f"nan-row/{vn}", require_bitwise=True)
-    assert st["mode_used"] == 2 and st["points_far"] > 0 and st["points_ring"] > 0 and st["points_brute"] > 0
-    assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == len(pts)
+    assert st["mode_used"] == 2 and st["points_far"] > 0 and st["points_ring"] + st["points_tree"] >= 3000 and st["points_tree"] > 0
+    assert st["points_brute"] == 0
+    assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == len(pts)
 
 
 @pytest.mark.parametrize("vn", ["A", "B"])
 def test_crowded_voxels_and_noise_clouds(eng, vn):
     """Tiles longer than the in-kernel sort (thousands of twigs in one voxel: unsorted fallback, many staging
     chunks), a dense cluster of duplicates, and a cloud that is mostly far from every cylinder (far part of the
-    tiles, ball-query ring search with and without an incumbent)."""
+    tiles, tree search with and without an incumbent)."""
     base = make_case(600, 20_000, seed=61, variant=vn)
     rng = np.random.default_rng(62)
     k = 3000
@@ -305,8 +308,8 @@ def test_crowded_voxels_and_noise_clouds(eng, vn):
         assert_parity(got, ora, f"crowded/{vn}/{mode}", require_bitwise=True)
         if mode == "grid":
             st = eng.stats()
-            assert st["points_far"] > 0 and st["points_ring"] > 0
-            assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == len(pts)
+            assert st["points_far"] > 0 and st["points_tree"] > 30_000 and st["points_ring"] == 0      # many stragglers: tree search
+            assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == len(pts)
 
 
 # ---- full-size properties ---------------------------------------------------------------------------------
@@ -327,7 +330,8 @@ def test_full_size_properties(eng, n, m):
     dpts = torch.tensor(pts, device=dev)
     full = eng.label(dpts, api.VARIANT_A, mode="grid", want=("index", "id", "dist", "offset"))
     st = eng.stats()
-    assert st["mode_used"] == 2 and st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_brute"] == n
+    assert st["mode_used"] == 2 and st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == n
+    assert st["points_ring"] > 0 and st["points_tree"] == 0                                        # few stragglers: ring search
     rng = np.random.default_rng(3)
     sub = torch.tensor(rng.choice(n, 20_000, replace=False), device=dev)
     brute = eng.label(dpts[sub], api.VARIANT_A, mode="brute", want=("index", "id", "dist", "offset"))
