@@ -339,6 +339,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N_POINTS * e2e_steps / float(te.item()) if e2e_steps else None
+    pipe = eng.host_pipeline_info() if e2e_steps else {"d2h_bytes_per_point": 16, "host_threads": None}
     e2e_ok = bool((rec_np[:1000, 6] == out["id"][:1000].cpu().numpy()).all()) if e2e_steps else None
 
     if rank != 0:
@@ -401,8 +402,10 @@ def main():
                    "cell_size_m": stats.get("cell_size"), "l2": "flushed between steps (256 MiB write)",
                    "parallelism": f"points sharded x{world}, cylinder table broadcast once"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * 12, "d2h_bytes_per_step": N_POINTS * 56,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * 12, "d2h_bytes_per_step": N_POINTS * pipe["d2h_bytes_per_point"],
                 "api": "Engine.label_cloud_host (tm_label_cloud_host): pinned fp32 cloud -> pinned (N,7) float64 records",
+                "host_assembly_threads": pipe["host_threads"],
+                "note": "with host_assembly_threads > 0 only {offset, id} (16 B/point) cross PCIe; the host workers write the 56 B records",
                 "steps": e2e_steps, "checked": e2e_ok},
         "gpu_launches": launches_per_step * steps,
         "roofline": roofline, "fp32_roofline": fp32_roofline, "brute_force_yardstick": brute,

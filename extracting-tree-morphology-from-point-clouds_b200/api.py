@@ -254,6 +254,12 @@ class Engine:
             out.append(index)
         return out[0] if len(out) == 1 else tuple(out)
 
+    def host_pipeline_info(self) -> dict:
+        """D2H bytes per point and host worker threads of the last ``label_cloud_host`` call."""
+        b, t = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self._lib.tm_host_pipeline_info(self._h, ctypes.byref(b), ctypes.byref(t)))
+        return {"d2h_bytes_per_point": int(b.value), "host_threads": int(t.value)}
+
     # -- introspection -----------------------------------------------------------------------
     def stats(self) -> dict:
         s = B.TmStats()

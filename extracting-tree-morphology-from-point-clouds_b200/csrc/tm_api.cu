@@ -4,11 +4,17 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
 
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "tm_core.cuh"
 #include "tm_eval.cuh"
@@ -206,6 +212,59 @@ __global__ void selftest_kernel(uint64_t n, uint32_t seed, unsigned long long *_
 
 }  // namespace tmn
 
+// Persistent host workers (created on first use, joined in tm_destroy).  run(fn) executes fn(worker, workers) on
+// every worker including the calling thread and returns when all are done.
+struct tmn::HostPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    std::function<void(unsigned, unsigned)> job;
+    uint64_t generation = 0;
+    unsigned pending = 0, n = 1;
+    bool stop = false;
+    explicit HostPool(unsigned nthreads) : n(std::max(1u, nthreads)) {
+        for (unsigned t = 1; t < n; ++t)
+            workers.emplace_back([this, t] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::function<void(unsigned, unsigned)> fn;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv_job.wait(lk, [&] { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        fn = job;
+                    }
+                    fn(t, n);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) cv_done.notify_one();
+                    }
+                }
+            });
+    }
+    void run(const std::function<void(unsigned, unsigned)> &fn) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = fn;
+            pending = n - 1;
+            ++generation;
+        }
+        cv_job.notify_all();
+        fn(0, n);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (auto &t : workers) t.join();
+    }
+};
+
 using namespace tmn;
 
 extern "C" {
@@ -258,6 +317,8 @@ int tm_destroy(tm_handle *h) {
         if (h->pinned_out[i]) cudaFreeHost(h->pinned_out[i]);
     }
     if (h->small_stream) cudaStreamDestroy(h->small_stream);
+    delete h->pool;
+    for (auto &b : h->chunk_packed) b.release();
     for (auto &s : h->pipe_stream) if (s) cudaStreamDestroy(s);
     for (auto &e : h->pipe_event) if (e) cudaEventDestroy(e);
     for (auto &e : h->phase_ev) if (e) cudaEventDestroy(e);
@@ -419,6 +480,169 @@ static bool host_is_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost;
 }
 
+static unsigned host_threads_available() {
+    cpu_set_t set;
+    unsigned avail = 0;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = static_cast<unsigned>(CPU_COUNT(&set));
+    if (avail == 0) avail = std::thread::hardware_concurrency();
+    return std::max(1u, avail);
+}
+
+}  // extern "C" (reopened below)
+
+// (N,7) float64 rows [x, y, z, ox, oy, oz, ID] (LabelGenerationCuda.py:114,131-133) written by the HOST: xyz come from
+// the caller's own cloud at its precision, only the 16-byte {offset, id} records cross PCIe.  Streaming stores: the
+// record array is written once and never read here.
+static inline void store_f64(double *dst, double v) {
+#if defined(__x86_64__)
+    long long bits;
+    memcpy(&bits, &v, 8);
+    _mm_stream_si64(reinterpret_cast<long long *>(dst), bits);
+#else
+    *dst = v;
+#endif
+}
+
+template <typename T>
+static void assemble_rows_host(const T *cloud, int64_t row_stride, const float4 *packed, double *out, int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; ++r) {
+        const T *p = cloud + r * row_stride;
+        const float4 k = packed[r];
+        int32_t id;
+        memcpy(&id, &k.w, 4);
+        double *o = out + 7 * r;
+        store_f64(o + 0, static_cast<double>(p[0]));
+        store_f64(o + 1, static_cast<double>(p[1]));
+        store_f64(o + 2, static_cast<double>(p[2]));
+        store_f64(o + 3, static_cast<double>(k.x));
+        store_f64(o + 4, static_cast<double>(k.y));
+        store_f64(o + 5, static_cast<double>(k.z));
+        store_f64(o + 6, static_cast<double>(id));
+    }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+}
+
+// tm_label_cloud_host, host-assembly variant: per chunk H2D -> label (packed {offset, id}) -> D2H 16 B/point, while the
+// host workers assemble the previous chunk's records.
+static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride,
+                                     const tm_params *params, double *out_records_host, float *out_dist_host, unsigned nthreads) {
+    if (!h->pool || h->pool->n != nthreads) {
+        delete h->pool;
+        h->pool = new (std::nothrow) tmn::HostPool(nthreads);
+        if (!h->pool) return tmn::fail(h, TM_ERR_NOMEM, "host worker pool%s%s");
+    }
+    cudaStream_t s_in = h->pipe_stream[0], s_cmp = h->pipe_stream[1], s_out = h->pipe_stream[2];
+    h->host_d2h_bytes_per_point = 16 + (out_dist_host ? 4 : 0);
+    h->host_assembly_threads = static_cast<int32_t>(nthreads);
+    int64_t chunk = 1 << 20;
+    if (const char *env = getenv("TM_HOST_CHUNK")) { const long long v = atoll(env); if (v >= 1024) chunk = v; }
+    chunk = std::min(chunk, n);
+    const size_t esz = dtype == TM_F32 ? 4 : 8;
+    const bool in_pinned = host_is_pinned(cloud_host);
+    const size_t in_bytes = static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+    const size_t pk_bytes = static_cast<size_t>(chunk) * sizeof(float4);
+    const size_t out_bytes = pk_bytes + static_cast<size_t>(chunk) * sizeof(float);
+    for (int b = 0; b < 2; ++b) {
+        if (!in_pinned && h->pinned_in_cap < in_bytes) {
+            if (h->pinned_in[b]) { cudaFreeHost(h->pinned_in[b]); h->pinned_in[b] = nullptr; }
+            TM_CUDA(h, cudaMallocHost(&h->pinned_in[b], in_bytes));
+        }
+        if (h->pinned_out_cap < out_bytes) {
+            if (h->pinned_out[b]) { cudaFreeHost(h->pinned_out[b]); h->pinned_out[b] = nullptr; }
+            TM_CUDA(h, cudaMallocHost(&h->pinned_out[b], out_bytes));
+        }
+        TM_CUDA(h, h->chunk_in[b].ensure(in_bytes + (dtype == TM_F64 ? static_cast<size_t>(chunk) * 12 : 0)));
+        TM_CUDA(h, h->chunk_packed[b].ensure(pk_bytes));
+        TM_CUDA(h, h->chunk_dist[b].ensure(static_cast<size_t>(chunk) * 4));
+    }
+    if (!in_pinned) h->pinned_in_cap = std::max(h->pinned_in_cap, in_bytes);
+    h->pinned_out_cap = std::max(h->pinned_out_cap, out_bytes);
+
+    // events: [0,1] H2D done per buffer, [2,3] compute done, [4,5] D2H done
+    tm_stats total{};
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const unsigned char *src = static_cast<const unsigned char *>(cloud_host);
+    auto assemble = [&](int64_t c) -> int {
+        const int b = static_cast<int>(c & 1);
+        const int64_t cnt = std::min(chunk, n - c * chunk);
+        TM_CUDA(h, cudaEventSynchronize(h->pipe_event[4 + b]));
+        const float4 *packed = static_cast<const float4 *>(h->pinned_out[b]);
+        const unsigned char *crow = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+        double *orow = out_records_host + c * chunk * 7;
+        h->pool->run([=](unsigned t, unsigned nt) {
+            const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
+            if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1);
+            else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1);
+        });
+        if (out_dist_host)
+            memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b]) + pk_bytes, static_cast<size_t>(cnt) * sizeof(float));
+        return TM_OK;
+    };
+    int rc = TM_OK;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = static_cast<int>(c & 1);
+        const int64_t cnt = std::min(chunk, n - c * chunk);
+        const size_t bytes = static_cast<size_t>(cnt) * static_cast<size_t>(row_stride) * esz;
+        const unsigned char *csrc = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+        // buffers b were last used by chunk c-2, which was assembled (hence fully transferred) in iteration c-1
+        if (!in_pinned) {
+            par_memcpy(h->pinned_in[b], csrc, bytes);
+            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b], bytes, cudaMemcpyHostToDevice, s_in));
+        } else {
+            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
+        }
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[0 + b], s_in));
+        TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[0 + b], 0));
+        const float *pts32;
+        int64_t stride32;
+        if (dtype == TM_F64) {
+            float *conv = reinterpret_cast<float *>(h->chunk_in[b].as<unsigned char>() + in_bytes);
+            const int blocks = static_cast<int>(std::min<int64_t>((cnt * 3 + 255) / 256, static_cast<int64_t>(h->sm_count) * 32));
+            f64_to_f32_xyz_kernel<<<blocks, 256, 0, s_cmp>>>(h->chunk_in[b].as<double>(), cnt, row_stride, conv);
+            TM_CUDA(h, cudaGetLastError());
+            pts32 = conv;
+            stride32 = 3;
+        } else {
+            pts32 = h->chunk_in[b].as<float>();
+            stride32 = row_stride;
+        }
+        h->stats = tm_stats{};
+        LabelArgs a{pts32, cnt, stride32, *params, nullptr, nullptr, out_dist_host ? h->chunk_dist[b].as<float>() : nullptr,
+                    nullptr, nullptr, s_cmp};
+        a.out_packed = h->chunk_packed[b].as<float4>();
+        rc = label_dispatch(h, a);
+        if (rc != TM_OK) return rc;
+        total.pairs_evaluated += h->stats.pairs_evaluated;
+        total.points_brute += h->stats.points_brute;
+        h->last_n = cnt;
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[2 + b], s_cmp));
+        TM_CUDA(h, cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
+        TM_CUDA(h, cudaMemcpyAsync(h->pinned_out[b], h->chunk_packed[b].p, static_cast<size_t>(cnt) * sizeof(float4),
+                                   cudaMemcpyDeviceToHost, s_out));
+        if (out_dist_host)
+            TM_CUDA(h, cudaMemcpyAsync(static_cast<unsigned char *>(h->pinned_out[b]) + pk_bytes, h->chunk_dist[b].p,
+                                       static_cast<size_t>(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[4 + b], s_out));
+        if (c >= 1) {
+            // the s_cmp work of chunk c must not overwrite chunk_packed / chunk_in of chunk c+1's buffer pair before the
+            // transfers of chunk c-1 are done: assembling c-1 here (it waits for its D2H) gives exactly that order
+            rc = assemble(c - 1);
+            if (rc != TM_OK) return rc;
+        }
+    }
+    rc = assemble(nchunks - 1);
+    if (rc != TM_OK) return rc;
+    TM_CUDA(h, cudaStreamSynchronize(s_cmp));
+    h->stats.pairs_evaluated = total.pairs_evaluated;
+    h->stats.points_brute = total.points_brute;
+    return TM_OK;
+}
+
+extern "C" {
+
+
 int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride,
                         const tm_params *params, double *out_records_host, float *out_dist_host) {
     if (!h) return TM_ERR_INVALID;
@@ -435,6 +659,19 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
     for (auto &e : h->pipe_event) if (!e) TM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     cudaStream_t s_in = h->pipe_stream[0], s_cmp = h->pipe_stream[1], s_out = h->pipe_stream[2];
 
+    // With a few host threads to spare the records are assembled on the host: only 16 bytes per point come back over PCIe
+    // instead of 56, and the host writes the xyz it already has.  TM_HOST_ASSEMBLE=0 forces the device-assembled path.
+    {
+        const char *env = getenv("TM_HOST_ASSEMBLE");
+        const int want = env ? atoi(env) : -1;
+        const unsigned ht = std::min(host_threads_available(), 16u);
+        if (want != 0 && (ht >= 4 || want > 0))
+            return label_cloud_host_assemble(h, cloud_host, dtype, n, row_stride, params, out_records_host, out_dist_host,
+                                             want > 0 ? std::max(1u, std::min(static_cast<unsigned>(want), 64u)) : ht);
+    }
+
+    h->host_d2h_bytes_per_point = 56 + (out_dist_host ? 4 : 0);
+    h->host_assembly_threads = 0;
     int64_t chunk = 1 << 20;
     if (const char *env = getenv("TM_HOST_CHUNK")) { const long long v = atoll(env); if (v >= 1024) chunk = v; }
     chunk = std::min(chunk, n);
@@ -644,6 +881,13 @@ int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
     h->stats.mode_used = TM_MODE_BRUTE;
     h->stats.pairs_evaluated = static_cast<uint64_t>(n) * static_cast<uint64_t>(m);
     h->stats.points_brute = static_cast<uint64_t>(n);
+    return TM_OK;
+}
+
+int tm_host_pipeline_info(tm_handle *h, int32_t *d2h_bytes_per_point, int32_t *host_threads) {
+    if (!h) return TM_ERR_INVALID;
+    if (d2h_bytes_per_point) *d2h_bytes_per_point = h->host_d2h_bytes_per_point;
+    if (host_threads) *host_threads = h->host_assembly_threads;
     return TM_OK;
 }
 

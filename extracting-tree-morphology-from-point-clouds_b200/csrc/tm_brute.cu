@@ -121,7 +121,7 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
                 const float4 *__restrict__ recA, const float4 *__restrict__ recB, const int32_t *__restrict__ ids,
                 float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index,
                 int32_t *__restrict__ out_id, float *__restrict__ out_dist, float *__restrict__ out_offset,
-                float *__restrict__ out_radius) {
+                float *__restrict__ out_radius, float4 *__restrict__ out_packed) {
     const int64_t n_eff = d_count ? static_cast<int64_t>(*d_count) : n;
     for (int64_t slot = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; slot < n_eff;
          slot += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -139,6 +139,7 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
         if (out_dist) out_dist[row] = g.dist;
         if (out_offset) { out_offset[3 * row] = ox; out_offset[3 * row + 1] = oy; out_offset[3 * row + 2] = oz; }
         if (out_radius) out_radius[row] = b.w;
+        if (out_packed) out_packed[row] = make_float4(ox, oy, oz, __int_as_float(ids[j]));
     }
 }
 
@@ -294,7 +295,7 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
     finalize_kernel<G, F><<<fgrid, 256, 0, a.stream>>>(a.pts, n_launch, a.row_stride, sel, d_count, keys, A, B,     \
                                                        h->ids.as<int32_t>(), a.prm.perp_atol, a.prm.norm_eps,       \
                                                        a.prm.move_to_mantle, a.out_index, a.out_id, a.out_dist,     \
-                                                       a.out_offset, a.out_radius)
+                                                       a.out_offset, a.out_radius, a.out_packed)
     if (guard) { if (nfma) TM_FIN_CASE(true, true); else TM_FIN_CASE(true, false); }
     else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
 #undef TM_FIN_CASE
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, const int32_t *__restrict__ win,
                      const float4 *__restrict__ recAB, const int32_t *__restrict__ ids,
                      float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index, int32_t *__restrict__ out_id,
-                     float *__restrict__ out_dist, float *__restrict__ out_offset, float *__restrict__ out_radius) {
+                     float *__restrict__ out_dist, float *__restrict__ out_offset, float *__restrict__ out_radius,
+                     float4 *__restrict__ out_packed) {
     // two rows per thread and iteration: both rows' loads (point, winning row, then the dependent record gathers) are in
     // flight together, which is what hides the L2 latency of the gathers
     constexpr int R = 2;
@@ -350,7 +352,7 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
         float4 a[R], b[R];
         int32_t id[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) { a[k] = recAB[2 * j[k]]; b[k] = recAB[2 * j[k] + 1]; id[k] = out_id ? ids[j[k]] : 0; }
+        for (int k = 0; k < R; ++k) { a[k] = recAB[2 * j[k]]; b[k] = recAB[2 * j[k] + 1]; id[k] = (out_id || out_packed) ? ids[j[k]] : 0; }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             PairGeom g;
@@ -364,6 +366,7 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
             if (out_dist) out_dist[r] = g.dist;
             if (out_offset) { out_offset[3 * r] = ox; out_offset[3 * r + 1] = oy; out_offset[3 * r + 2] = oz; }
             if (out_radius) out_radius[r] = b[k].w;
+            if (out_packed) out_packed[r] = make_float4(ox, oy, oz, __int_as_float(id[k]));
         }
     }
 }
@@ -375,7 +378,7 @@ int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win) {
     finalize_rows_kernel<G, F><<<grid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, win, h->recAB.as<float4>(),     \
                                                            h->ids.as<int32_t>(), a.prm.perp_atol,                       \
                                                            a.prm.norm_eps, a.prm.move_to_mantle, a.out_index, a.out_id, \
-                                                           a.out_dist, a.out_offset, a.out_radius)
+                                                           a.out_dist, a.out_offset, a.out_radius, a.out_packed)
     if (guard) { if (nfma) TM_FINR_CASE(true, true); else TM_FINR_CASE(true, false); }
     else       { if (nfma) TM_FINR_CASE(false, true); else TM_FINR_CASE(false, false); }
 #undef TM_FINR_CASE

@@ -60,6 +60,8 @@ struct DevStats {
     unsigned int pad[1];
 };
 
+struct HostPool;                     // tm_api.cu
+
 }  // namespace tmn
 
 struct tm_handle {
@@ -128,6 +130,10 @@ struct tm_handle {
     tmn::DevBuf small_out;           // per call: flags (u8) | dist (f32) | index (i32)
     cudaStream_t small_stream = nullptr;
 
+    tmn::HostPool *pool = nullptr;   // host worker threads that assemble the (N,7) float64 records
+    int32_t host_d2h_bytes_per_point = 0, host_assembly_threads = 0;     // what the last tm_label_cloud_host call did
+    tmn::DevBuf chunk_packed[2];
+
     // ---- optional phase timing ----
     bool profiling = false;
     cudaEvent_t phase_ev[TM_PHASES + 1] = {nullptr};
@@ -186,6 +192,7 @@ struct LabelArgs {
     float *out_offset;
     float *out_radius;
     cudaStream_t stream;
+    float4 *out_packed = nullptr;    // optional {offset.xyz, bits(id)} per row (the host-assembly path of tm_label_cloud_host)
 };
 
 // tm_brute.cu

@@ -156,7 +156,7 @@ int tm_assemble_records(tm_handle *h, const void *cloud, int32_t cloud_dtype, in
  * Projection.py:117-144): chunks the cloud, overlaps H2D copy / labelling / record assembly / D2H
  * on internal streams, and writes the (N,7) float64 record to out_records_host.
  * cloud_host: (N, >=3) TM_F32 or TM_F64, row stride in elements.  out_dist_host (N,) may be NULL.
- * Host buffers may be pageable; pinned buffers avoid a staging copy.  Synchronous.
+ * Host buffers may be pageable; a pinned cloud avoids a staging copy.  Synchronous.
  */
 int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t cloud_dtype, int64_t n,
                         int64_t cloud_row_stride, const tm_params *params,
@@ -182,6 +182,14 @@ int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
                             const float *start_host, const float *end_host, const float *radius_host, int64_t m,
                             const tm_params *params, float axis_eps, float eps,
                             uint8_t *out_flags_host, float *out_dist_host, int32_t *out_index_host);
+
+/*
+ * How the last tm_label_cloud_host call moved its results: with >= 4 host threads available the (N,7) float64 records are
+ * assembled by host worker threads (xyz from the caller's own cloud, 16 bytes of {offset, id} per point over PCIe;
+ * *host_threads = workers used); otherwise the device assembles them and 56 bytes per point come back (*host_threads = 0).
+ * TM_HOST_ASSEMBLE=0 in the environment forces the latter, =k forces k workers.
+ */
+int tm_host_pipeline_info(tm_handle *h, int32_t *d2h_bytes_per_point, int32_t *host_threads);
 
 /* Counters of the last labelling call.  Synchronises the device. */
 int tm_get_stats(tm_handle *h, tm_stats *out);

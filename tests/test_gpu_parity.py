@@ -312,6 +312,30 @@ def test_crowded_voxels_and_noise_clouds(eng, vn):
             assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == len(pts)
 
 
+@pytest.mark.parametrize("f64", [False, True])
+def test_host_pipeline_variants_agree(eng, f64, monkeypatch):
+    """tm_label_cloud_host: host-assembled records (16 B/point over PCIe) and device-assembled records (56 B/point) are
+    the same bits, for pageable clouds with extra columns, several chunks and a ragged tail, and equal the oracle."""
+    case = make_case(900, 70_001, seed=71, variant="B")
+    _install(eng, case)
+    pts = case["points"]
+    cloud = np.concatenate([pts.astype(np.float64) if f64 else pts, np.full((len(pts), 2), 7, pts.dtype if not f64 else np.float64)], axis=1)
+    ora = oracle_label(case, pts)
+    monkeypatch.setenv("TM_HOST_CHUNK", "16384")
+    outs = {}
+    for mode in ("0", "3", "16"):
+        monkeypatch.setenv("TM_HOST_ASSEMBLE", mode)
+        rec, dist = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid", want_dist=True)
+        info = eng.host_pipeline_info()
+        assert info["host_threads"] == int(mode) and info["d2h_bytes_per_point"] == (60 if mode == "0" else 20)
+        outs[mode] = (rec, dist)
+        assert np.array_equal(rec[:, :3], cloud[:, :3].astype(np.float64))
+        assert np.array_equal(rec[:, 3:6], ora["offset"].astype(np.float64), equal_nan=True)
+        assert np.array_equal(rec[:, 6], ora["id"].astype(np.float64))
+        assert np.array_equal(dist, ora["dist"], equal_nan=True)
+    assert np.array_equal(outs["0"][0], outs["3"][0], equal_nan=True) and np.array_equal(outs["0"][0], outs["16"][0], equal_nan=True)
+
+
 # ---- full-size properties ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,m", [(1_000_000, 10_000), (10_000_000, 50_000)])
