@@ -392,7 +392,7 @@ def main():
                "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {host_threads()} threads "
                          f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
 
-    launches_per_step = {"grid": 10, "auto": 10, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, tree search, exhaustive, pending winners, epilogue
+    launches_per_step = {"grid": 11, "auto": 11, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, ring, tree search, exhaustive, pending winners, epilogue
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -485,6 +485,8 @@ static unsigned host_threads_available() {
     unsigned avail = 0;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = static_cast<unsigned>(CPU_COUNT(&set));
     if (avail == 0) avail = std::thread::hardware_concurrency();
+    // one process per GPU (torchrun): the ranks of a node share the host cores
+    if (const char *lws = getenv("LOCAL_WORLD_SIZE")) { const int r = atoi(lws); if (r > 1) avail /= static_cast<unsigned>(r); }
     return std::max(1u, avail);
 }
 

@@ -312,6 +312,29 @@ def test_crowded_voxels_and_noise_clouds(eng, vn):
             assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == len(pts)
 
 
+@pytest.mark.parametrize("shift", [(1000.0, -2500.0, 300.0), (4.0e5, 5.6e6, 120.0)])
+def test_projected_coordinates(eng, shift):
+    """Plots in projected (national grid / UTM-like) coordinates: fp32 world coordinates are coarse there (1e-4 .. 0.5 m
+    per ulp), the reference's answers are what they are, and the pruning must still reproduce them exactly."""
+    from treemorph_b200 import synth
+    q = synth.random_qsm(1200, seed=91)
+    for k in ("startX", "endX"):
+        q[k] = q[k] + shift[0]
+    for k in ("startY", "endY"):
+        q[k] = q[k] + shift[1]
+    for k in ("startZ", "endZ"):
+        q[k] = q[k] + shift[2]
+    pts = synth.sample_points(q, 30_000, seed=92)
+    start, radius, length, unit, ids = synth.cylinder_arrays(q)
+    case = {"start": start, "radius": radius, "length": length, "unit": unit, "ids": ids, "variant": _oracle.VARIANT_A, "points": pts}
+    with np.errstate(all="ignore"):
+        ora = oracle_label(case, pts)
+        _install(eng, case)
+        for mode in ("grid", "brute"):
+            got = _label(eng, case, pts, mode)
+            assert_parity(got, ora, f"shifted{shift}/{mode}", require_bitwise=True)
+
+
 @pytest.mark.parametrize("f64", [False, True])
 def test_host_pipeline_variants_agree(eng, f64, monkeypatch):
     """tm_label_cloud_host: host-assembled records (16 B/point over PCIe) and device-assembled records (56 B/point) are
