@@ -3,6 +3,8 @@
 
     python scripts/bench_configs.py --out gpurun_out/configs.json [--max-points 100000000] [--skip-sweep]
 
+config 1 : single tree, 100k points x 2k cylinders (the reference's own CPU-runnable case): device resident, through the
+           LabelGenerationCuda drop-in, and the oracle port on the host cores; all 100k rows compared bit-for-bit.
 config 2 : 1M points x 10k cylinders, variants A and B, labels + offsets, device resident; checked against the
            oracle on a subsample.
 config 4 : 5M PTv3-style corrected points x 50k cylinders through the Projection drop-in
@@ -87,6 +89,34 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     res = {"gpu": torch.cuda.get_device_name(0), "host_cpus": os.cpu_count()}
     want = ("index", "id", "dist", "offset")
+
+    # ---- config 1: single tree, 100k points x 2k cylinders, label generation; EVERY point checked against the oracle
+    qsm = synth.random_qsm(2_000, seed=1)
+    pts = synth.sample_points(qsm, 100_000, seed=2)
+    arrs = synth.cylinder_arrays(qsm)
+    install(eng, torch, arrs)
+    dpts = torch.tensor(pts, device=dev)
+    med, best = timed(torch, lambda: eng.label(dpts, api.VARIANT_A, mode="auto", want=want), flush)
+    full = {k: v.cpu().numpy() for k, v in eng.label(dpts, api.VARIANT_A, mode="auto", want=want).items()}
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        ora = oracle.label(pts, *arrs, oracle.VARIANT_A)
+    cpu_s = time.perf_counter() - t0
+    from treemorph_b200.PreProcessing import LabelGenerationCuda
+    df = synth.qsm_dataframe(qsm)
+    LabelGenerationCuda.generate_offset_cloud_cuda_batched(pts.astype(np.float64), df, dev)
+    t0 = time.perf_counter()
+    rec = LabelGenerationCuda.generate_offset_cloud_cuda_batched(pts.astype(np.float64), df, dev)
+    api_s = time.perf_counter() - t0
+    res["config1"] = {"points": 100_000, "cylinders": 2_000, "device_resident_ms": med, "points_per_s": 1e5 / (med * 1e-3),
+                      "dropin_generate_offset_cloud_ms": api_s * 1e3,
+                      "oracle_port_cpu_s": cpu_s, "oracle_threads": oracle.max_threads(),
+                      "reference_cpu_s_in_build_container": "~165 s on 8 threads (SURVEY.md B.4)",
+                      "all_rows_bitwise_equal_to_oracle": bool((full["index"] == ora["index"]).all() and np.array_equal(full["dist"], ora["dist"], equal_nan=True)
+                                                               and np.array_equal(full["offset"], ora["offset"], equal_nan=True)
+                                                               and np.array_equal(rec[:, 3:6], ora["offset"].astype(np.float64), equal_nan=True)
+                                                               and np.array_equal(rec[:, 6], ora["id"].astype(np.float64)))}
+    print("config1", json.dumps(res["config1"]), flush=True)
 
     # ---- config 2
     qsm = synth.random_qsm(10_000, seed=1)
