@@ -359,6 +359,57 @@ def test_host_pipeline_variants_agree(eng, f64, monkeypatch):
     assert np.array_equal(outs["0"][0], outs["3"][0], equal_nan=True) and np.array_equal(outs["0"][0], outs["16"][0], equal_nan=True)
 
 
+def _fuzz_case(rng):
+    """Random cylinder tables well outside the synthetic-tree regime: scales from millimetres to tens of metres, needles
+    and discs, clusters, zero-length / zero-radius / duplicated cylinders, optional NaN rows; points near, far, on axes."""
+    m = int(rng.choice([1, 2, 5, 37, 300, 2500]))
+    scale = float(10.0 ** rng.uniform(-2.5, 1.3))
+    centre = rng.normal(0, 1, 3) * float(10.0 ** rng.uniform(-1, 2.5))
+    start = centre + rng.normal(0, 1, (m, 3)) * scale * rng.choice([0.3, 3.0, 30.0])
+    d = rng.normal(size=(m, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    length = np.abs(rng.normal(0, 1, m)) * scale * rng.choice([0.1, 1.0, 10.0])
+    radius = np.abs(rng.normal(0, 1, m)) * scale * rng.choice([0.01, 0.2, 2.0])
+    if m > 4:
+        length[rng.integers(m)] = 0.0                      # zero-length cylinder (NaN unit in variant A)
+        radius[rng.integers(m)] = 0.0
+        k = rng.integers(1, m)
+        start[k], d[k], length[k], radius[k] = start[0], d[0], length[0], radius[0]      # exact duplicate: lowest row wins
+        d[rng.integers(m)] = [0.0, 0.0, 1.0]               # axis-parallel
+    end = start + d * length[:, None]
+    n = int(rng.choice([1, 33, 1000, 20_000]))
+    pick = rng.integers(0, m, n)
+    t = rng.uniform(-0.3, 1.3, n)
+    base = start[pick] + (end[pick] - start[pick]) * t[:, None]
+    noise = rng.normal(size=(n, 3)) * (radius[pick][:, None] + scale * rng.choice([0.01, 0.3, 5.0]))
+    pts = base + noise
+    on_axis = rng.random(n) < 0.05
+    pts[on_axis] = base[on_axis]                           # exactly on an axis line / inside a cylinder
+    far = rng.random(n) < 0.05
+    pts[far] += rng.normal(size=(int(far.sum()), 3)) * scale * 300
+    return start.astype(np.float32), end.astype(np.float32), radius.astype(np.float32), pts.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_grid_equals_exhaustive_equals_oracle(eng, seed):
+    rng = np.random.default_rng(1000 + seed)
+    start, end, radius, pts = _fuzz_case(rng)
+    vn = "AB"[seed % 2]
+    var = _oracle.VARIANTS[vn]
+    with np.errstate(all="ignore"):
+        length, unit = _oracle.prepare(start, end, var)
+    ids = (rng.permutation(len(start)) + 5).astype(np.int32)
+    case = {"start": start, "radius": radius, "length": length, "unit": unit, "ids": ids, "variant": var, "points": pts}
+    with np.errstate(all="ignore"):
+        ora = oracle_label(case, pts)
+        _install(eng, case)
+        cell = float(rng.choice([0.0, 0.05, 0.4, 2.0]))
+        got_b = _label(eng, case, pts, "brute")
+        got_g = _label(eng, case, pts, "grid", cell_size=cell)
+    assert_parity(got_b, ora, f"fuzz{seed}/{vn}/brute", require_bitwise=True)
+    assert_parity(got_g, ora, f"fuzz{seed}/{vn}/grid(cell={cell})", require_bitwise=True)
+
+
 # ---- full-size properties ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,m", [(1_000_000, 10_000), (10_000_000, 50_000)])
