@@ -254,6 +254,29 @@ class Engine:
             out.append(index)
         return out[0] if len(out) == 1 else tuple(out)
 
+    # -- point-neighbourhood features (Modules/Features.py:111-172) ---------------------------------
+    def _f64_points(self, points) -> torch.Tensor:
+        pts = torch.as_tensor(np.ascontiguousarray(np.asarray(points)[:, :3], dtype=np.float64) if not isinstance(points, torch.Tensor)
+                              else points[:, :3])
+        return pts.to(device=self.device, dtype=torch.float64).contiguous()
+
+    def knn_covariance(self, points, k: int, want_idx: bool = False):
+        """np.cov of (k nearest neighbours - point) for every point → (N,3,3) float64 device tensor (+ (N,k) int32 rows)."""
+        pts = self._f64_points(points)
+        n = pts.shape[0]
+        cov = torch.empty((n, 3, 3), dtype=torch.float64, device=self.device)
+        idx = torch.empty((n, k), dtype=torch.int32, device=self.device) if want_idx else None
+        self._check(self._lib.tm_knn_covariance(self._h, _ptr(pts), n, 3, int(k), _ptr(cov), _ptr(idx), _stream_ptr(self.device)))
+        return (cov, idx) if want_idx else cov
+
+    def radius_count(self, points, radius: float) -> torch.Tensor:
+        """Number of points within ``radius`` of every point (itself included) → (N,) int32 device tensor."""
+        pts = self._f64_points(points)
+        n = pts.shape[0]
+        out = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._check(self._lib.tm_radius_count(self._h, _ptr(pts), n, 3, float(radius), _ptr(out), _stream_ptr(self.device)))
+        return out
+
     def host_pipeline_info(self) -> dict:
         """D2H bytes per point and host worker threads of the last ``label_cloud_host`` call."""
         b, t = ctypes.c_int32(), ctypes.c_int32()

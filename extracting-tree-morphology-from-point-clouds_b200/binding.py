@@ -57,6 +57,8 @@ SIGNATURES = {
     "tm_cloud_upload_host": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64]),
     "tm_proximity_flags_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(TmParams), c_f32,
                                                c_f32, c_vp, c_vp, c_vp]),
+    "tm_knn_covariance": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "tm_radius_count": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_double, c_vp, c_vp]),
     "tm_host_pipeline_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "tm_get_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(TmStats)]),
     "tm_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),

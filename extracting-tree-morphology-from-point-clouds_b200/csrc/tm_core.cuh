@@ -134,6 +134,9 @@ struct tm_handle {
     int32_t host_d2h_bytes_per_point = 0, host_assembly_threads = 0;     // what the last tm_label_cloud_host call did
     tmn::DevBuf chunk_packed[2];
 
+    // ---- point features (tm_knn.cu) ----
+    tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box;
+
     // ---- optional phase timing ----
     bool profiling = false;
     cudaEvent_t phase_ev[TM_PHASES + 1] = {nullptr};
@@ -216,6 +219,7 @@ struct SmallArgs {
     int32_t *index;
 };
 int run_proximity(tm_handle *h, const SmallArgs &a, bool guard, bool nfma, cudaStream_t st);
+int exclusive_scan_u32(tm_handle *h, const uint32_t *count, uint32_t n, uint32_t *start, cudaStream_t stream);
 // tm_bvh.cu
 int build_bvh(tm_handle *h, cudaStream_t stream);
 int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst);

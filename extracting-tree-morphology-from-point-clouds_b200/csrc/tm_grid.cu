@@ -372,6 +372,11 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
     return TM_OK;
 }
 
+// exclusive scan of `n` counters into start[0..n] (start[n] = total); used by the point-feature kernels (tm_knn.cu)
+int exclusive_scan_u32(tm_handle *h, const uint32_t *count, uint32_t n, uint32_t *start, cudaStream_t stream) {
+    return run_scan(h, count, n, 0, start, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: size the grid from the cylinders' bounding box and build the static tiles
 // ------------------------------------------------------------------------------------------------

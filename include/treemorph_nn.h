@@ -184,6 +184,23 @@ int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
                             uint8_t *out_flags_host, float *out_dist_host, int32_t *out_index_host);
 
 /*
+ * Point-neighbourhood features the drivers append right after the labelling (Modules/Features.py:178-229 at
+ * LabelGenerationCuda.py:197-198 / Projection.py:420-427), device side.  pts: float64 DEVICE array, row i at
+ * pts + i*row_stride, xyz contiguous (the labelled cloud is float64).
+ *
+ * tm_knn_covariance: for every point the k (2..32) nearest points of the same cloud, itself included (exact; ties by lower
+ *   row), and np.cov of (neighbours - point) (mean-subtracted, / (k-1)) as a row-major 3x3 in out_cov (n,9) — the matrix
+ *   compute_normals_ckdtree (:111-133, k = 15) feeds to the SVD and compute_curvature_ckdtree (:136-157, k = 10) to
+ *   eigvalsh.  out_idx (n,k) rows of the neighbours in ascending distance, may be NULL.
+ * tm_radius_count: len(tree.query_ball_point(point, r)) for every point (compute_density_ckdtree, :160-172).
+ * Both return TM_ERR_INVALID for non-finite coordinates or n < k.
+ */
+int tm_knn_covariance(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, int32_t k,
+                      double *out_cov, int32_t *out_idx, void *stream);
+int tm_radius_count(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, double radius,
+                    int32_t *out_count, void *stream);
+
+/*
  * How the last tm_label_cloud_host call moved its results: with >= 4 host threads available the (N,7) float64 records are
  * assembled by host worker threads (xyz from the caller's own cloud, 16 bytes of {offset, id} per point over PCIe;
  * *host_threads = workers used); otherwise the device assembles them and 56 bytes per point come back (*host_threads = 0).
