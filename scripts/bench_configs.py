@@ -185,6 +185,36 @@ def main():
         res["small_table"][f"rows_{n}"] = {"us_per_call": dt * 1e6, "calls_per_s": 1.0 / dt, "points_per_s": n / dt}
     print("small", json.dumps(res["small_table"]), flush=True)
 
+    # ---- feature step (Modules/Features.add_features as the drivers call it: normals k=15 + relative height)
+    from treemorph_b200.Modules import Features
+    qsm = synth.random_qsm(5000, seed=7)
+    res["features"] = {}
+    for n in (1_000_000, 10_000_000):
+        cloud = synth.sample_points(qsm, n, seed=8).astype(np.float64)
+        dp = torch.tensor(cloud, device=dev)
+        eng.knn_covariance(dp, 15)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eng.knn_covariance(dp, 15); b.record(); torch.cuda.synchronize()
+        knn_ms = a.elapsed_time(b)
+        a.record(); eng.radius_count(dp, 0.1); b.record(); torch.cuda.synchronize()
+        rc_ms = a.elapsed_time(b)
+        entry = {"knn15_covariance_device_ms": knn_ms, "radius_count_device_ms": rc_ms, "points_per_s_knn": n / (knn_ms * 1e-3)}
+        if n == 1_000_000:
+            lab = np.concatenate([cloud, np.zeros((n, 4))], axis=1)
+            t0 = time.perf_counter()
+            out = Features.add_features(lab, use_densities=False, use_curvatures=False, use_distances=False, use_verticalities=False)
+            entry["add_features_normals_height_s"] = time.perf_counter() - t0
+            entry["add_features_shape"] = list(out.shape)
+            from scipy.spatial import cKDTree
+            t0 = time.perf_counter()
+            tree = cKDTree(cloud[:100_000])
+            tree.query(cloud[:100_000], k=15)
+            entry["scipy_ckdtree_build_query_100k_s"] = time.perf_counter() - t0
+        res["features"][str(n)] = entry
+        del dp
+    print("features", json.dumps(res["features"]), flush=True)
+
     # ---- config 5 sweep
     if not args.skip_sweep:
         cells = []
