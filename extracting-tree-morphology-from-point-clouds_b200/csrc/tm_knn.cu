@@ -19,6 +19,7 @@
 //   output:  covariance (9 doubles) at the point's original row, optionally the neighbour rows.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "tm_core.cuh"
 
@@ -226,6 +227,7 @@ static int knn_build(tm_handle *h, const double *pts, int64_t n, int64_t row_str
     // so occupied cells end up with a handful of points each
     double ext[3], vol = 1.0;
     for (int k = 0; k < 3; ++k) { ext[k] = std::max(hi[k] - lo[k], 1e-9); vol *= ext[k]; }
+    if (const char *env = getenv("TM_KNN_BOX_PER_CELL")) { const double v = atof(env); if (v >= 0.01 && v <= 256.0) pts_per_cell = v; }
     double hcell = std::cbrt(vol * pts_per_cell / static_cast<double>(n));
     const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
     hcell = std::max(hcell, longest / 2048.0);
@@ -254,8 +256,10 @@ static int knn_build(tm_handle *h, const double *pts, int64_t n, int64_t row_str
         TM_CUDA(h, cudaMemcpyAsync(&occ, h->knn_box.as<long long>() + 7, sizeof(occ), cudaMemcpyDeviceToHost, st));
         TM_CUDA(h, cudaStreamSynchronize(st));
         const double per_occ = static_cast<double>(n) / std::max(1u, occ);
-        if (per_occ <= 2.0 * pts_per_cell * 4.0) break;
-        hcell = std::max(hcell * std::sqrt(4.0 * pts_per_cell / per_occ), longest / 2048.0);
+        double target = 12.0;
+        if (const char *env = getenv("TM_KNN_PER_CELL")) { const double v = atof(env); if (v >= 0.5 && v <= 256.0) target = v; }
+        if (per_occ <= 2.0 * target) break;
+        hcell = std::max(hcell * std::sqrt(target / per_occ), longest / 2048.0);
     }
     TM_CUDA(h, h->knn_start.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncells) + 1)));
     TM_CUDA(h, h->knn_sorted.ensure(sizeof(double4) * static_cast<size_t>(n)));
