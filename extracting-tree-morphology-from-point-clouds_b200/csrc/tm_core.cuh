@@ -103,7 +103,6 @@ struct tm_handle {
 
     // ---- per-call scratch ----
     tmn::DevBuf keys;                // u64 per point (brute mode) / per pending slot (grid mode)
-    tmn::DevBuf pt_cell, pt_rank;    // uint32 per point
     tmn::DevBuf cell_count, cell_start, block_sums;      // index build (cell_count / cell_start) and scan partials
     tmn::DevBuf cells;               // uint2 per voxel: {point count -> scatter cursor, first sorted point}
     tmn::DevBuf sorted_pts;          // float4 per point {x,y,z,bits(original row)}
@@ -135,7 +134,7 @@ struct tm_handle {
     tmn::DevBuf chunk_packed[2];
 
     // ---- point features (tm_knn.cu) ----
-    tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box;
+    tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box, knn_retry[2];
 
     // ---- optional phase timing ----
     bool profiling = false;
