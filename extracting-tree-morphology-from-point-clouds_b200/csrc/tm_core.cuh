@@ -134,7 +134,7 @@ struct tm_handle {
     tmn::DevBuf chunk_packed[2];
 
     // ---- point features (tm_knn.cu) ----
-    tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box, knn_retry[2];
+    tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box;
 
     // ---- optional phase timing ----
     bool profiling = false;

@@ -101,19 +101,12 @@ __global__ void __launch_bounds__(256) knn_scatter_kernel(const double *__restri
 
 constexpr int KNN_MAX = 32;
 
-// exact k nearest neighbours + covariance, one thread per query (in cell order: neighbouring threads walk the same
-// cells).  queries == nullptr: every point of the grid is a query; else the listed {x, y, z, bits(row)} records.
-// A query that has not converged after `ring_limit` rings (an isolated point: its neighbours are many cells away) is
-// appended to `retry` and answered on a coarser grid by the next launch; the last level runs without a limit.
-__global__ void __launch_bounds__(128) knn_cov_kernel(const double4 *__restrict__ sorted, const uint32_t *__restrict__ start,
-                                                      const double4 *__restrict__ queries, const unsigned int *__restrict__ n_queries_dev,
-                                                      int64_t n_queries, KnnGrid g, int k, int ring_limit, double4 *__restrict__ retry,
-                                                      unsigned int *__restrict__ n_retry, double *__restrict__ out_cov,
-                                                      int32_t *__restrict__ out_idx) {
+// exact k nearest neighbours + covariance, one thread per point (in cell order: neighbouring threads walk the same cells)
+__global__ void __launch_bounds__(128) knn_cov_kernel(const double4 *__restrict__ sorted, const uint32_t *__restrict__ start, int64_t n,
+                                                      KnnGrid g, int k, double *__restrict__ out_cov, int32_t *__restrict__ out_idx) {
     const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t nq = n_queries_dev ? static_cast<int64_t>(*n_queries_dev) : n_queries;
-    if (t >= nq) return;
-    const double4 q = queries ? queries[t] : sorted[t];
+    if (t >= n) return;
+    const double4 q = sorted[t];
     const int64_t row = __double_as_longlong(q.w);
     const int cx = knn_coord(q.x, g.ox, g.inv_h, g.nx), cy = knn_coord(q.y, g.oy, g.inv_h, g.ny), cz = knn_coord(q.z, g.oz, g.inv_h, g.nz);
     double bd[KNN_MAX];
@@ -161,10 +154,6 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const double4 *__restrict_
             if (bd[k - 1] <= bound * bound) break;
         }
         if (z0 == 0 && y0 == 0 && x0 == 0 && z1 == g.nz - 1 && y1 == g.ny - 1 && x1 == g.nx - 1) break;     // whole grid visited
-        if (r == ring_limit) {                         // isolated point: hand it to the next, coarser level
-            retry[atomicAdd(n_retry, 1u)] = q;
-            return;
-        }
     }
     // np.cov of (neighbours - point): rows = coordinates, mean-subtracted, / (k - 1)   (Features.py:127-128)
     double mx = 0, my = 0, mz = 0;
@@ -217,10 +206,10 @@ __global__ void __launch_bounds__(256) knn_occupied_kernel(const uint32_t *__res
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(occ, mine);
 }
 
-struct KnnBox { double lo[3], ext[3], longest; };
-
-static int knn_bbox(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, KnnBox *out, cudaStream_t st) {
-    TM_CUDA(h, h->knn_box.ensure(sizeof(long long) * 16));
+// bounding box -> grid -> counting sort.  min_cell: lower bound on the cell edge (radius search), 0 = automatic.
+static int knn_build(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, double min_cell, double pts_per_cell, KnnGrid *out,
+                     cudaStream_t st) {
+    TM_CUDA(h, h->knn_box.ensure(sizeof(long long) * 8));
     const long long init[8] = {0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL,
                                static_cast<long long>(0x8000000000000000ULL), static_cast<long long>(0x8000000000000000ULL),
                                static_cast<long long>(0x8000000000000000ULL), 0, 0};
@@ -232,35 +221,46 @@ static int knn_bbox(tm_handle *h, const double *pts, int64_t n, int64_t row_stri
     TM_CUDA(h, cudaMemcpyAsync(box, h->knn_box.p, sizeof(box), cudaMemcpyDeviceToHost, st));
     TM_CUDA(h, cudaStreamSynchronize(st));
     if (box[6] != 0) return fail(h, TM_ERR_INVALID, "point features: the cloud holds non-finite coordinates%s%s");
-    out->longest = 0.0;
-    for (int k = 0; k < 3; ++k) {
-        out->lo[k] = ordered_to_double(box[k]);
-        out->ext[k] = std::max(ordered_to_double(box[3 + k]) - out->lo[k], 1e-9);
-        out->longest = std::max(out->longest, out->ext[k]);
-    }
-    return TM_OK;
-}
-
-static KnnGrid knn_grid_for(const KnnBox &b, double &hcell) {
+    double lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) { lo[k] = ordered_to_double(box[k]); hi[k] = ordered_to_double(box[3 + k]); }
+    // cell edge: pts_per_cell points per cell if the cloud filled its box; surface-like clouds fill a few per cent of it,
+    // so occupied cells end up with a handful of points each
+    double ext[3], vol = 1.0;
+    for (int k = 0; k < 3; ++k) { ext[k] = std::max(hi[k] - lo[k], 1e-9); vol *= ext[k]; }
+    if (const char *env = getenv("TM_KNN_BOX_PER_CELL")) { const double v = atof(env); if (v >= 0.01 && v <= 256.0) pts_per_cell = v; }
+    double hcell = std::cbrt(vol * pts_per_cell / static_cast<double>(n));
+    const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
+    hcell = std::max(hcell, longest / 2048.0);
+    hcell = std::max(hcell, min_cell);
     KnnGrid g;
-    for (;;) {
-        g.nx = static_cast<int>(b.ext[0] / hcell) + 1; g.ny = static_cast<int>(b.ext[1] / hcell) + 1; g.nz = static_cast<int>(b.ext[2] / hcell) + 1;
-        if (static_cast<double>(g.nx) * g.ny * g.nz <= static_cast<double>(1u << 27)) break;
-        hcell *= 1.26;
+    uint32_t ncells = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (;;) {
+            g.nx = static_cast<int>(ext[0] / hcell) + 1; g.ny = static_cast<int>(ext[1] / hcell) + 1; g.nz = static_cast<int>(ext[2] / hcell) + 1;
+            if (static_cast<double>(g.nx) * g.ny * g.nz <= static_cast<double>(1u << 27)) break;
+            hcell *= 1.26;
+        }
+        g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.h = hcell; g.inv_h = 1.0 / hcell;
+        ncells = static_cast<uint32_t>(g.nx) * g.ny * g.nz;
+        TM_CUDA(h, h->knn_cells.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncells) + 1)));
+        TM_CUDA(h, cudaMemsetAsync(h->knn_cells.p, 0, sizeof(uint32_t) * ncells, st));
+        knn_count_kernel<<<blocks, 256, 0, st>>>(pts, n, row_stride, g, h->knn_cells.as<uint32_t>());
+        TM_KCHECK(h, st, "knn_count_kernel");
+        if (pass == 1 || min_cell > 0.0) break;
+        // a surface-sampled cloud fills a few per cent of its box: measure the points per OCCUPIED cell and shrink the
+        // edge (points per occupied cell of a surface go with h^2) until there are a handful
+        unsigned int occ = 0;
+        TM_CUDA(h, cudaMemsetAsync(h->knn_box.as<long long>() + 7, 0, sizeof(long long), st));
+        knn_occupied_kernel<<<h->sm_count * 8, 256, 0, st>>>(h->knn_cells.as<uint32_t>(), ncells,
+                                                             reinterpret_cast<unsigned int *>(h->knn_box.as<long long>() + 7));
+        TM_CUDA(h, cudaMemcpyAsync(&occ, h->knn_box.as<long long>() + 7, sizeof(occ), cudaMemcpyDeviceToHost, st));
+        TM_CUDA(h, cudaStreamSynchronize(st));
+        const double per_occ = static_cast<double>(n) / std::max(1u, occ);
+        double target = 12.0;
+        if (const char *env = getenv("TM_KNN_PER_CELL")) { const double v = atof(env); if (v >= 0.5 && v <= 256.0) target = v; }
+        if (per_occ <= 2.0 * target) break;
+        hcell = std::max(hcell * std::sqrt(target / per_occ), longest / 2048.0);
     }
-    g.ox = b.lo[0]; g.oy = b.lo[1]; g.oz = b.lo[2]; g.h = hcell; g.inv_h = 1.0 / hcell;
-    return g;
-}
-
-// counting sort of the cloud by the cells of `g`; count_only stops after the occupancy pass
-static int knn_sort(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, const KnnGrid &g, bool count_only, cudaStream_t st) {
-    const uint32_t ncells = static_cast<uint32_t>(g.nx) * g.ny * g.nz;
-    const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(h->sm_count) * 16));
-    TM_CUDA(h, h->knn_cells.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncells) + 1)));
-    TM_CUDA(h, cudaMemsetAsync(h->knn_cells.p, 0, sizeof(uint32_t) * ncells, st));
-    knn_count_kernel<<<blocks, 256, 0, st>>>(pts, n, row_stride, g, h->knn_cells.as<uint32_t>());
-    TM_KCHECK(h, st, "knn_count_kernel");
-    if (count_only) return TM_OK;
     TM_CUDA(h, h->knn_start.ensure(sizeof(uint32_t) * (static_cast<size_t>(ncells) + 1)));
     TM_CUDA(h, h->knn_sorted.ensure(sizeof(double4) * static_cast<size_t>(n)));
     int rc = exclusive_scan_u32(h, h->knn_cells.as<uint32_t>(), ncells, h->knn_start.as<uint32_t>(), st);
@@ -269,32 +269,7 @@ static int knn_sort(tm_handle *h, const double *pts, int64_t n, int64_t row_stri
     knn_scatter_kernel<<<blocks, 256, 0, st>>>(pts, n, row_stride, g, h->knn_cells.as<uint32_t>(), h->knn_start.as<uint32_t>(),
                                                h->knn_sorted.as<double4>());
     TM_KCHECK(h, st, "knn_scatter_kernel");
-    return TM_OK;
-}
-
-// cell edge for the neighbour search: one point per cell if the cloud filled its box; a surface-sampled cloud fills a few
-// per cent of it, so the points per OCCUPIED cell are measured and the edge shrunk (they go with h^2 on a surface) until
-// there are about a dozen
-static int knn_auto_cell(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, const KnnBox &b, double *out_h, cudaStream_t st) {
-    double vol = b.ext[0] * b.ext[1] * b.ext[2];
-    double per_box_cell = 1.0;
-    if (const char *env = getenv("TM_KNN_BOX_PER_CELL")) { const double v = atof(env); if (v >= 0.01 && v <= 256.0) per_box_cell = v; }
-    double hcell = std::max(std::cbrt(vol * per_box_cell / static_cast<double>(n)), b.longest / 2048.0);
-    KnnGrid g = knn_grid_for(b, hcell);
-    int rc = knn_sort(h, pts, n, row_stride, g, true, st);
-    if (rc != TM_OK) return rc;
-    const uint32_t ncells = static_cast<uint32_t>(g.nx) * g.ny * g.nz;
-    unsigned int occ = 0;
-    unsigned int *d_occ = reinterpret_cast<unsigned int *>(h->knn_box.as<long long>() + 8);
-    TM_CUDA(h, cudaMemsetAsync(d_occ, 0, sizeof(unsigned int), st));
-    knn_occupied_kernel<<<h->sm_count * 8, 256, 0, st>>>(h->knn_cells.as<uint32_t>(), ncells, d_occ);
-    TM_CUDA(h, cudaMemcpyAsync(&occ, d_occ, sizeof(occ), cudaMemcpyDeviceToHost, st));
-    TM_CUDA(h, cudaStreamSynchronize(st));
-    const double per_occ = static_cast<double>(n) / std::max(1u, occ);
-    double target = 12.0;
-    if (const char *env = getenv("TM_KNN_PER_CELL")) { const double v = atof(env); if (v >= 0.5 && v <= 256.0) target = v; }
-    if (per_occ > 2.0 * target) hcell = std::max(hcell * std::sqrt(target / per_occ), b.longest / 2048.0);
-    *out_h = hcell;
+    *out = g;
     return TM_OK;
 }
 
@@ -314,40 +289,12 @@ int tm_knn_covariance(tm_handle *h, const double *pts, int64_t n, int64_t row_st
     if (n > 0x7fffffffLL) return fail(h, TM_ERR_INVALID, "tm_knn_covariance: more than 2^31-1 points%s%s");
     TM_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    KnnBox box;
-    int rc = knn_bbox(h, pts, n, row_stride, &box, st);
+    KnnGrid g;
+    int rc = knn_build(h, pts, n, row_stride, 0.0, 1.0, &g, st);
     if (rc != TM_OK) return rc;
-    double hcell = 0.0;
-    rc = knn_auto_cell(h, pts, n, row_stride, box, &hcell, st);
-    if (rc != TM_OK) return rc;
-    // levels: the fine grid answers the bulk within 2 rings; isolated points (noise far from any surface) would walk
-    // hundreds of empty cells there, so they are retried on grids 4x, 16x, ... coarser; the last level has no ring limit
-    TM_CUDA(h, h->knn_retry[0].ensure(sizeof(double4) * static_cast<size_t>(n)));
-    unsigned int *d_cnt = reinterpret_cast<unsigned int *>(h->knn_box.as<long long>() + 9);      // two counters
-    TM_CUDA(h, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), st));
-    constexpr int LEVELS = 4;
-    int64_t nq = n;
-    for (int level = 0; level < LEVELS && nq > 0; ++level) {
-        KnnGrid g = knn_grid_for(box, hcell);
-        rc = knn_sort(h, pts, n, row_stride, g, false, st);
-        if (rc != TM_OK) return rc;
-        const bool whole = static_cast<int64_t>(g.nx) * g.ny * g.nz == 1;
-        const bool last = level == LEVELS - 1 || whole;
-        const int in = level & 1, out = in ^ 1;
-        if (!last) TM_CUDA(h, h->knn_retry[out].ensure(sizeof(double4) * static_cast<size_t>(nq)));
-        TM_CUDA(h, cudaMemsetAsync(d_cnt + out, 0, sizeof(unsigned int), st));
-        knn_cov_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(
-            h->knn_sorted.as<double4>(), h->knn_start.as<uint32_t>(), level == 0 ? nullptr : h->knn_retry[in].as<double4>(),
-            level == 0 ? nullptr : d_cnt + in, nq, g, k, last ? 0x7fffffff : 2, last ? nullptr : h->knn_retry[out].as<double4>(),
-            d_cnt + out, out_cov, out_idx);
-        TM_KCHECK(h, st, "knn_cov_kernel");
-        if (last) break;
-        unsigned int left = 0;
-        TM_CUDA(h, cudaMemcpyAsync(&left, d_cnt + out, sizeof(left), cudaMemcpyDeviceToHost, st));
-        TM_CUDA(h, cudaStreamSynchronize(st));
-        nq = left;
-        hcell *= 4.0;
-    }
+    knn_cov_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(h->knn_sorted.as<double4>(), h->knn_start.as<uint32_t>(), n, g, k,
+                                                                         out_cov, out_idx);
+    TM_KCHECK(h, st, "knn_cov_kernel");
     return TM_OK;
 }
 
@@ -359,12 +306,8 @@ int tm_radius_count(tm_handle *h, const double *pts, int64_t n, int64_t row_stri
     if (n > 0x7fffffffLL) return fail(h, TM_ERR_INVALID, "tm_radius_count: more than 2^31-1 points%s%s");
     TM_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    KnnBox box;
-    int rc = knn_bbox(h, pts, n, row_stride, &box, st);
-    if (rc != TM_OK) return rc;
-    double hcell = std::max(radius * (1.0 + 1e-9), box.longest / 2048.0);       // cell edge >= radius: 27 cells cover the ball
-    KnnGrid g = knn_grid_for(box, hcell);
-    rc = knn_sort(h, pts, n, row_stride, g, false, st);
+    KnnGrid g;
+    int rc = knn_build(h, pts, n, row_stride, radius * (1.0 + 1e-9), 1.0, &g, st);
     if (rc != TM_OK) return rc;
     radius_count_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(h->knn_sorted.as<double4>(), h->knn_start.as<uint32_t>(), n, g,
                                                                               radius, out_count);
