@@ -527,41 +527,69 @@ __device__ __forceinline__ uint32_t point_code(const GridDev &g, float x, float 
     return inside ? voxel_code(g, static_cast<int>(fx), static_cast<int>(fy), static_cast<int>(fz)) : NO_CELL;
 }
 
+// Both passes aggregate inside the warp first (MATCH.ANY on the voxel id): lanes that hit the same voxel elect a leader
+// that issues ONE atomic for the group.  A randomly ordered cloud gains nothing (no two lanes share a voxel, the match
+// costs a few instructions next to an L2 atomic); a spatially coherent one — tiled exports, scan lines, re-labelling a
+// sorted cloud — sends up to 32x fewer atomics.
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
                                                         uint2 *__restrict__ cells, int32_t *__restrict__ pend_idx,
                                                         unsigned long long *__restrict__ pend_keys,
                                                         uint32_t *__restrict__ brute_slots, DevStats *__restrict__ st) {
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float *p = pts + i * row_stride;
-        const float x = p[0], y = p[1], z = p[2];
-        const uint32_t code = point_code(g, x, y, z);
-        if (code != NO_CELL) {
-            atomicAdd(&cells[code].x, 1u);
-        } else {
-            // outside the grid: straight to the tree search; non-finite coordinates cannot be bounded at all and take the
-            // exhaustive kernel
-            const unsigned int s = atomicAdd(&st->pending, 1u);
-            pend_idx[s] = static_cast<int32_t>(i) | OUTSIDE_BIT;
-            pend_keys[s] = KEY_NONE;
-            if (!(fabsf(x) + fabsf(y) + fabsf(z) < 3.0e38f)) brute_slots[atomicAdd(&st->n_brute, 1u)] = s;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t base = blockIdx.x * static_cast<int64_t>(blockDim.x) + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t i = base + lane;
+        uint32_t code = NO_CELL - 1u - static_cast<uint32_t>(lane);       // idle lanes: distinct ids that match nobody
+        bool valid = false;
+        if (i < n) {
+            const float *p = pts + i * row_stride;
+            const float x = p[0], y = p[1], z = p[2];
+            const uint32_t c = point_code(g, x, y, z);
+            if (c != NO_CELL) {
+                code = c;
+                valid = true;
+            } else {
+                // outside the grid: straight to the tree search; non-finite coordinates cannot be bounded at all and take
+                // the exhaustive kernel
+                const unsigned int s = atomicAdd(&st->pending, 1u);
+                pend_idx[s] = static_cast<int32_t>(i) | OUTSIDE_BIT;
+                pend_keys[s] = KEY_NONE;
+                if (!(fabsf(x) + fabsf(y) + fabsf(z) < 3.0e38f)) brute_slots[atomicAdd(&st->n_brute, 1u)] = s;
+            }
         }
+        const uint32_t peers = __match_any_sync(0xffffffffu, code);
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&cells[code].x, static_cast<uint32_t>(__popc(peers)));
     }
 }
 
-// pass 2: each point takes the next free slot of its voxel's run.  A cell is {cursor, run start}: one 64-bit atomic
-// increments the cursor and returns both words (one L2 request instead of an atomic plus a gather).
+// pass 2: each point takes the next free slot of its voxel's run.  A cell is {cursor, run start}: one 64-bit atomic per
+// group of lanes advances the cursor by the group size and returns both words.
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
                                                           uint2 *__restrict__ cells, float4 *__restrict__ sorted) {
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float *p = pts + i * row_stride;
-        const float x = p[0], y = p[1], z = p[2];
-        const uint32_t code = point_code(g, x, y, z);
-        if (code == NO_CELL) continue;
-        const unsigned long long cell = atomicAdd(reinterpret_cast<unsigned long long *>(cells + code), 1ull);
-        const uint32_t pos = static_cast<uint32_t>(cell >> 32) + static_cast<uint32_t>(cell);
-        sorted[pos] = make_float4(x, y, z, __int_as_float(static_cast<int>(i)));
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t base = blockIdx.x * static_cast<int64_t>(blockDim.x) + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t i = base + lane;
+        uint32_t code = NO_CELL - 1u - static_cast<uint32_t>(lane);
+        bool valid = false;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < n) {
+            const float *p = pts + i * row_stride;
+            x = p[0]; y = p[1]; z = p[2];
+            const uint32_t c = point_code(g, x, y, z);
+            if (c != NO_CELL) { code = c; valid = true; }
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, code);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long cell = 0;
+        if (valid && lane == leader)
+            cell = atomicAdd(reinterpret_cast<unsigned long long *>(cells + code), static_cast<unsigned long long>(__popc(peers)));
+        cell = __shfl_sync(0xffffffffu, cell, leader);
+        if (valid) {
+            const uint32_t pos = static_cast<uint32_t>(cell >> 32) + static_cast<uint32_t>(cell) + static_cast<uint32_t>(__popc(peers & lt));
+            sorted[pos] = make_float4(x, y, z, __int_as_float(static_cast<int>(i)));
+        }
     }
 }
 
