@@ -76,7 +76,8 @@ struct tm_handle {
     tmn::DevBuf recAB;               // float4[2M]: the same records interleaved (one 32-byte sector per cylinder: gathers)
     tmn::DevBuf ids;                 // int32[M]
     tmn::DevBuf boxlo, boxhi;        // float4[M]: solid-cylinder AABB (w unused)
-    tmn::DevBuf bbox;                // 6 floats as ordered ints: global min/max + counters
+    tmn::DevBuf bbox;                // 6 floats as ordered ints: global min/max + counters + size statistics
+    float mean_extent = 0.f;        // mean (length + diameter) of the regular cylinders
 
     // ---- static voxel index of the cylinders (per table and cell size) ----
     bool have_grid = false;
