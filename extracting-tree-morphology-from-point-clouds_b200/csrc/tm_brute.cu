@@ -163,7 +163,7 @@ struct BruteCullArgs {
     int m;
     const int32_t *special, *aligned;
     uint32_t n_special, n_aligned;
-    float atol, eps, maxabs;
+    float atol, eps, maxabs, slack_floor;
     unsigned long long *keys;
     DevStats *st;
 };
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) brute_cull_kernel(BruteCullArgs a) {
         const float *p = a.pts + static_cast<int64_t>(a.pend_idx[slot] & 0x7fffffff) * a.row_stride;
         const float px = p[0], py = p[1], pz = p[2];
         // rounding allowance at this point's own coordinate scale (inf / NaN coordinates: nothing is culled)
-        const float slack = 1e-4f + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
+        const float slack = a.slack_floor + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
         const unsigned long long key0 = a.keys[slot];          // incumbent from the other chunks (may be stale)
         unsigned long long best = KEY_NONE;
         float thr = thr_of(key0, slack);
@@ -397,7 +397,7 @@ int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win
     b.m = static_cast<int>(h->m);
     b.special = h->special.as<int32_t>(); b.aligned = h->aligned.as<int32_t>();
     b.n_special = h->n_special; b.n_aligned = h->n_aligned;
-    b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = maxabs;
+    b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = maxabs; b.slack_floor = h->slack_floor;
     b.keys = h->keys.as<unsigned long long>();
     b.st = dst;
     const int wgrid = h->sm_count * 8;

@@ -164,7 +164,7 @@ struct BvhArgs {
     const float4 *recA, *recB;
     const int32_t *special, *aligned;
     uint32_t n_special, n_aligned;
-    float atol, eps, maxabs;
+    float atol, eps, maxabs, slack_floor;
     DevStats *st;
 };
 
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) bvh_kernel(BvhArgs a) {
         if (!(fabsf(px) + fabsf(py) + fabsf(pz) < 3.0e38f)) continue;      // non-finite: the exhaustive kernel's
         unsigned long long key = a.pend_keys[slot];
         if (static_cast<uint32_t>(key >> 32) == 0u) continue;              // NaN incumbent is final
-        const float slack = 1e-4f + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
+        const float slack = a.slack_floor + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
         if (ri < 0) {
             // outside the grid: the tile kernel never saw this point
             for (uint32_t e = 0; e < a.n_special; ++e) {
@@ -286,7 +286,7 @@ int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst) {
     b.recA = h->recA.as<float4>(); b.recB = h->recB.as<float4>();
     b.special = h->special.as<int32_t>(); b.aligned = h->aligned.as<int32_t>();
     b.n_special = h->n_special; b.n_aligned = h->n_aligned;
-    b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = h->maxabs;
+    b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = h->maxabs; b.slack_floor = h->slack_floor;
     b.st = dst;
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
     const int grid = h->sm_count * 16;

@@ -85,6 +85,7 @@ struct tm_handle {
     float reach = 0.f;              // D_max: tile(V) holds every cylinder whose capsule comes within D_max of voxel V
     float near = 0.f;               // D_near: the leading `near` entries of a tile are those within D_near of the voxel
     float maxabs = 0.f;             // largest |coordinate| of the grid (scales the rounding slack)
+    float slack_floor = 1e-4f;      // absolute part of the rounding slack (proportional to the voxel edge below tree scale)
     tmn::GridDesc grid{};
     tmn::DevBuf cyl_cell_start;      // uint32[ncell_codes + 1]: first pool entry of each voxel's tile (multiple of 4)
     tmn::DevBuf cyl_cell_cnt;        // uint32[ncell_codes]: tile length

@@ -403,7 +403,10 @@ float auto_cell_size(const tm_handle *h, int64_t) {
 }
 
 // rounding allowance of the reference's fp32 pipeline (and of the bound arithmetic) at coordinate scale `maxabs`
-static inline float slack_for(float maxabs) { return 1e-4f + 4e-6f * maxabs; }
+// The relative term covers ~30 ulp of the largest coordinate in play; the floor (0.1 mm at tree scale, proportional to the
+// voxel edge for smaller models) is head-room on top of it.
+static inline float slack_floor_for(float h) { return std::min(1e-4f, 4e-4f * h); }
+static inline float slack_for(float maxabs, float h) { return slack_floor_for(h) + 4e-6f * maxabs; }
 
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     // global bounding box of the regular cylinders' AABBs (written by pack_kernel as ordered ints)
@@ -459,7 +462,8 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     float maxabs = 0.f;
     for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, std::max(std::fabs(lo[k]), std::fabs(hi[k])) + margin);
     h->maxabs = maxabs;
-    const GridDev g = to_dev(d, slack_for(maxabs), h->reach, h->near);
+    h->slack_floor = slack_floor_for(hcell);
+    const GridDev g = to_dev(d, slack_for(maxabs, hcell), h->reach, h->near);
 
     const int m = static_cast<int>(h->m);
     const uint32_t ncodes = d.ncell_codes;
@@ -1078,7 +1082,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     h->stats.mode_used = TM_MODE_GRID;
     if (h->n_listed == 0 && h->n_long == 0) return label_brute(h, a);     // only special cylinders: nothing to prune with
 
-    const float slack = slack_for(h->maxabs);
+    const float slack = slack_for(h->maxabs, h->grid.h);
     const GridDev g = to_dev(h->grid, slack, h->reach, h->near);
     const uint32_t ncodes = h->grid.ncell_codes;
     const size_t n = static_cast<size_t>(a.n);

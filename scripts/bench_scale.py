@@ -1,4 +1,4 @@
-"""The same 1M x 10k workload in different UNITS (model scaled by 0.01 / 1 / 100): the automatic voxel edge follows the
+"""The same 1M x 10k workload in different UNITS (model scaled by 0.001 / 0.01 / 1 / 100): the automatic voxel edge follows the
 cylinder sizes, so the step time must not depend on the unit.  Each run is checked against the exhaustive kernel."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +10,7 @@ eng = api.Engine(dev)
 qsm = synth.random_qsm(10_000, seed=1)
 pts0 = synth.sample_points(qsm, 1_000_000, seed=2).astype(np.float64)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for scale in (0.01, 1.0, 100.0):
+for scale in (0.001, 0.01, 1.0, 100.0):
     q = {k: (np.asarray(v) * scale if k != "ID" else v) for k, v in qsm.items()}
     s, r, l, u, i = synth.cylinder_arrays(q)
     eng.set_cylinders(*(torch.tensor(x, device=dev) for x in (s, r, l, u)), torch.tensor(i, device=dev))
