@@ -98,9 +98,10 @@ __global__ void pack_kernel(const float *__restrict__ start, int64_t s_rs, int64
     atomicMin(&bbox[0], float_to_ordered(lx)); atomicMin(&bbox[1], float_to_ordered(ly)); atomicMin(&bbox[2], float_to_ordered(lz));
     atomicMax(&bbox[3], float_to_ordered(hx)); atomicMax(&bbox[4], float_to_ordered(hy)); atomicMax(&bbox[5], float_to_ordered(hz));
     atomicAdd(&bbox[7], 1);
-    // size statistics for the automatic voxel edge: sum of (length + diameter) in 2^-20 m units (integer: order independent)
-    atomicAdd(reinterpret_cast<unsigned long long *>(bbox + 10),
-              static_cast<unsigned long long>(fminf(len + 2.f * ar, 1.0e6f) * 1048576.0f));
+    // size statistics for the automatic voxel edge: sums of the lengths and of the diameters in 2^-20 m units (integers:
+    // order independent, so the edge does not change from run to run)
+    atomicAdd(reinterpret_cast<unsigned long long *>(bbox + 10), static_cast<unsigned long long>(fminf(len, 1.0e6f) * 1048576.0f));
+    atomicAdd(reinterpret_cast<unsigned long long *>(bbox + 12), static_cast<unsigned long long>(fminf(2.f * ar, 1.0e6f) * 1048576.0f));
     // axis-parallel (two exactly-zero unit components): NaN for every point on the axis line in variant A
     if ((ux == 0.f) + (uy == 0.f) + (uz == 0.f) >= 2) aligned[atomicAdd(&bbox[8], 1)] = c;
 }
@@ -368,10 +369,10 @@ int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_c
     TM_CUDA(h, h->boxhi.ensure(sizeof(float4) * mm));
     TM_CUDA(h, h->special.ensure(sizeof(int32_t) * mm));
     TM_CUDA(h, h->aligned.ensure(sizeof(int32_t) * mm));
-    TM_CUDA(h, h->bbox.ensure(sizeof(int) * 12));
+    TM_CUDA(h, h->bbox.ensure(sizeof(int) * 14));
     // [0..2] min corner, [3..5] max corner (ordered ints), [6] special, [7] regular, [8] axis-parallel
-    const int init[12] = {0x7fffffff, 0x7fffffff, 0x7fffffff, static_cast<int>(0x80000000), static_cast<int>(0x80000000),
-                          static_cast<int>(0x80000000), 0, 0, 0, 0, 0, 0};
+    const int init[14] = {0x7fffffff, 0x7fffffff, 0x7fffffff, static_cast<int>(0x80000000), static_cast<int>(0x80000000),
+                          static_cast<int>(0x80000000), 0, 0, 0, 0, 0, 0, 0, 0};
     TM_CUDA(h, cudaMemcpyAsync(h->bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const int blocks = static_cast<int>((m + 127) / 128);
     pack_kernel<<<blocks, 128, 0, st>>>(start, s_rs, s_cs, unit, u_rs, u_cs, length, l_s, radius, r_s, ids, i_s,
@@ -380,12 +381,17 @@ int tm_set_cylinders(tm_handle *h, const float *start, int64_t s_rs, int64_t s_c
                                         h->boxlo.as<float4>(), h->boxhi.as<float4>(), h->bbox.as<int>(),
                                         h->special.as<int32_t>(), h->aligned.as<int32_t>());
     TM_CUDA(h, cudaGetLastError());
-    int stat[12];
+    int stat[14];
     TM_CUDA(h, cudaMemcpyAsync(stat, h->bbox.p, sizeof(stat), cudaMemcpyDeviceToHost, st));
     TM_CUDA(h, cudaStreamSynchronize(st));      // `init` is a stack buffer; also surfaces bad input pointers here
-    unsigned long long ext_sum;
-    memcpy(&ext_sum, stat + 10, sizeof(ext_sum));
-    h->mean_extent = stat[7] > 0 ? static_cast<float>(static_cast<double>(ext_sum) / 1048576.0 / stat[7]) : 0.f;
+    unsigned long long len_sum, dia_sum;
+    memcpy(&len_sum, stat + 10, sizeof(len_sum));
+    memcpy(&dia_sum, stat + 12, sizeof(dia_sum));
+    // what sets the number of cylinder pieces per voxel is the spacing along the branches, i.e. the cylinder LENGTH (a thick
+    // trunk and a twig of the same length load a voxel alike); the diameter only stands in for tables of zero-length pieces
+    const double mean_len = stat[7] > 0 ? static_cast<double>(len_sum) / 1048576.0 / stat[7] : 0.0;
+    const double mean_dia = stat[7] > 0 ? static_cast<double>(dia_sum) / 1048576.0 / stat[7] : 0.0;
+    h->mean_extent = static_cast<float>(mean_len > 0.0 ? mean_len : mean_dia);
     return TM_OK;
 }
 

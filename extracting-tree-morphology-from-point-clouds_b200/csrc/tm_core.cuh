@@ -77,7 +77,7 @@ struct tm_handle {
     tmn::DevBuf ids;                 // int32[M]
     tmn::DevBuf boxlo, boxhi;        // float4[M]: solid-cylinder AABB (w unused)
     tmn::DevBuf bbox;                // 6 floats as ordered ints: global min/max + counters + size statistics
-    float mean_extent = 0.f;        // mean (length + diameter) of the regular cylinders
+    float mean_extent = 0.f;        // mean length of the regular cylinders (mean diameter if all lengths are zero)
 
     // ---- static voxel index of the cylinders (per table and cell size) ----
     bool have_grid = false;

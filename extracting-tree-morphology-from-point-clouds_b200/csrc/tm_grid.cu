@@ -389,14 +389,14 @@ static inline float ordered_to_float(int k) {
 
 constexpr uint32_t MAX_CODES = 1u << 26;
 
-// Voxel edge when the caller does not choose one: 1.4 x the mean (length + diameter) of the cylinders, i.e. a voxel holds a
-// handful of cylinder pieces whatever the units or the scale of the model (0.25 m for tree QSMs with their ~0.2 m
-// cylinders: the measured optimum is flat between 0.2 and 0.3 m).  Two significant bits of mantissa are kept
+// Voxel edge when the caller does not choose one: 1.43 x the mean cylinder length, i.e. a voxel holds a handful of
+// cylinder pieces whatever the units or the scale of the model (0.25 m for tree QSMs with their ~0.175 m cylinders: the
+// measured optimum is flat between 0.2 and 0.3 m).  Two significant bits of mantissa are kept
 // so that the edge — and with it the static index — does not change with the last digits of the statistics.
 float auto_cell_size(const tm_handle *h, int64_t) {
     float e = h->mean_extent;
     if (!(e > 0.f) || !std::isfinite(e)) return 0.25f;
-    e = std::min(std::max(1.4f * e, 1e-5f), 1e5f);
+    e = std::min(std::max(1.43f * e, 1e-5f), 1e5f);
     int ex;
     const float mant = std::frexp(e, &ex);                 // e = mant * 2^ex, mant in [0.5, 1)
     return std::ldexp(std::round(mant * 8.f) / 8.f, ex);

@@ -116,9 +116,10 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const double4 *__restrict_
     const double fx = q.x - (g.ox + cx * g.h), fy = q.y - (g.oy + cy * g.h), fz = q.z - (g.oz + cz * g.h);
     const double margin = fmax(0.0, fmin(fmin(fmin(fx, g.h - fx), fmin(fy, g.h - fy)), fmin(fz, g.h - fz)));
     const int rmax = max(max(g.nx, g.ny), g.nz);
-    auto visit = [&](int x, int y, int z) {
-        const uint32_t c = (static_cast<uint32_t>(z) * g.ny + y) * g.nx + x;
-        for (uint32_t j = start[c], e = start[c + 1]; j < e; ++j) {
+    // candidates of the cells [xa, xb] of row (y, z): one contiguous run of the sorted array
+    auto visit = [&](int xa, int xb, int y, int z) {
+        const uint32_t row0 = (static_cast<uint32_t>(z) * g.ny + y) * g.nx;
+        for (uint32_t j = start[row0 + xa], e = start[row0 + xb + 1]; j < e; ++j) {
             const double4 p = sorted[j];
             const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
             const double d2 = dx * dx + dy * dy + dz * dz;
@@ -142,10 +143,10 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const double4 *__restrict_
         for (int z = z0; z <= z1; ++z) {
             for (int y = y0; y <= y1; ++y) {
                 if (abs(z - cz) == r || abs(y - cy) == r) {
-                    for (int x = x0; x <= x1; ++x) visit(x, y, z);          // a face of the shell
+                    visit(x0, x1, y, z);                                     // a face of the shell: the whole row
                 } else {                                                     // interior row: only its two end cells
-                    if (cx - r >= 0) visit(cx - r, y, z);
-                    if (cx + r < g.nx) visit(cx + r, y, z);
+                    if (cx - r >= 0) visit(cx - r, cx - r, y, z);
+                    if (cx + r < g.nx) visit(cx + r, cx + r, y, z);
                 }
             }
         }

@@ -239,7 +239,7 @@ def main():
                                       n_gpu=20_000, n_cpu=1_000 if m >= 50_000 else 2_000)
                 cell = {"points": n, "cylinders": m, "mode_used": {1: "brute", 2: "grid"}[st["mode_used"]], "ms_median": med,
                         "ms_min": best, "points_per_s": n / (med * 1e-3), "pairs_evaluated": st["pairs_evaluated"],
-                        "brute_equiv_pairs_per_s": n * m / (med * 1e-3), "points_ring": st["points_ring"], "points_tree": st["points_tree"],
+                        "cell_size": st["cell_size"], "brute_equiv_pairs_per_s": n * m / (med * 1e-3), "points_ring": st["points_ring"], "points_tree": st["points_tree"],
                         "points_brute": st["points_brute"], "check": chk}
                 cells.append(cell)
                 print("sweep", json.dumps(cell), flush=True)
