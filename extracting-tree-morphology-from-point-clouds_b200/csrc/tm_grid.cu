@@ -238,6 +238,8 @@ constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;     // 4096 voxels per block
 constexpr int PTS_PER_ITEM = 64;
+constexpr int CELL_PAD = 4;               // uint2 slots per voxel cell: one 32-byte sector each, so that neighbouring voxels'
+                                          // atomics do not queue up on a shared sector
 
 struct Tri { uint32_t a, b, c; };
 __device__ __forceinline__ Tri tri_add(Tri x, Tri y) { return Tri{x.a + y.a, x.b + y.b, x.c + y.c}; }
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         if (base + i < ncodes) {
             if (mode == 0) start[base + i] = run.a;
-            else *reinterpret_cast<uint2 *>(start + 2 * static_cast<size_t>(base + i)) = make_uint2(0u, run.a);
+            else *reinterpret_cast<uint2 *>(start + 2 * CELL_PAD * static_cast<size_t>(base + i)) = make_uint2(0u, run.a);
             if (mode == 1 && cnt[i]) {
                 const uint32_t toff = tile_start[base + i], tcnt = tile_cnt[base + i], tnear = tile_near[base + i];
                 const uint32_t far = tcnt - tnear;                       // < 2^24 (tile_sort_kernel)
@@ -364,7 +366,7 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
     Tri *bs = h->block_sums.as<Tri>();
-    const int stride = mode == 1 ? 2 : 1;
+    const int stride = mode == 1 ? 2 * CELL_PAD : 1;
     scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);
     scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);
     scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs, mode, start, tile_start, tile_cnt, tile_near, items);
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
             }
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, code);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&cells[code].x, static_cast<uint32_t>(__popc(peers)));
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&cells[static_cast<size_t>(code) * CELL_PAD].x, static_cast<uint32_t>(__popc(peers)));
     }
 }
 
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
         const int leader = __ffs(peers) - 1;
         unsigned long long cell = 0;
         if (valid && lane == leader)
-            cell = atomicAdd(reinterpret_cast<unsigned long long *>(cells + code), static_cast<unsigned long long>(__popc(peers)));
+            cell = atomicAdd(reinterpret_cast<unsigned long long *>(cells + static_cast<size_t>(code) * CELL_PAD), static_cast<unsigned long long>(__popc(peers)));
         cell = __shfl_sync(0xffffffffu, cell, leader);
         if (valid) {
             const uint32_t pos = static_cast<uint32_t>(cell >> 32) + static_cast<uint32_t>(cell) + static_cast<uint32_t>(__popc(peers & lt));
@@ -1090,7 +1092,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     // scratch
     const size_t max_occ = std::min<size_t>(n, ncodes);
     const size_t max_items = n / PTS_PER_ITEM + max_occ + 1;
-    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * (static_cast<size_t>(ncodes) + 1)));
+    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * CELL_PAD * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
     TM_CUDA(h, h->items.ensure(sizeof(uint4) * max_items));
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
@@ -1103,7 +1105,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
-    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * ncodes, st));
+    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * CELL_PAD * ncodes, st));
 
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
     bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cells.as<uint2>(),
