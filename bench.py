@@ -7,7 +7,9 @@
 Workload (config.workload): BASELINE.json configs[2] — a noise-augmented plot, 10M NoiseDataGeneration-style
 points against a 50k-cylinder QSM (10 synthetic trees), variant A (label generation).  One "step" labels the
 whole cloud once: device-resident fp32 points in, device-resident (index, id, distance, offset) out, including
-voxel binning, candidate-tile construction and the un-permuting write.  With N GPUs every rank labels its own
+everything that depends on the points (voxel binning / sort, tile kernel, ring / tree search, winner epilogue in input
+order); the per-table voxel index and BVH are built once before the timed region (reported as setup_ms).  The e2e leg
+goes through the host API: pinned fp32 cloud in, (N,7) float64 records out, copies inside the timed region.  With N GPUs every rank labels its own
 10M-point cloud against the same table, which rank 0 broadcasts once over NCCL (weak scaling, no data-path
 collective).  Prints ONE JSON line on rank 0.
 
@@ -382,7 +384,7 @@ def main():
 
     # ---- reference algorithm on the host cores, bounded sample, same run
     cpu = None
-    if not args.skip_cpu:
+    if not args.skip_cpu and world == 1:          # the contract: rank 0 at N = 1 only
         from oracle import oracle
         oracle.build()
         n_s, _ = cpu_sample_size(12.0, qsm, pts_host, oracle.VARIANT_A)
