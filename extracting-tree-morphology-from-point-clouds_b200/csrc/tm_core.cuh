@@ -102,6 +102,7 @@ struct tm_handle {
     tmn::DevBuf bvh_leafAB;          // float4[2 x count]: records in leaf order
     int32_t bvh_root = 0, bvh_count = 0;
     uint64_t index_entries = 0;
+    uint32_t voxels_with_tiles = 0;  // voxels within D_max of some cylinder (density estimate for the point sort)
 
     // ---- per-call scratch ----
     tmn::DevBuf keys;                // u64 per point (brute mode) / per pending slot (grid mode)

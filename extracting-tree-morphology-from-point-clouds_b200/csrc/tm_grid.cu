@@ -165,14 +165,17 @@ __global__ void __launch_bounds__(SORT_WARPS * 32)
 tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_cnt, uint32_t ncodes,
                  const unsigned long long *__restrict__ tile_keys, const float4 *__restrict__ recA,
                  const float4 *__restrict__ recB, float near_reach, float4 *__restrict__ tileA, float4 *__restrict__ tileB,
-                 int32_t *__restrict__ tileI, float *__restrict__ tileLB, uint32_t *__restrict__ cell_near) {
+                 int32_t *__restrict__ tileI, float *__restrict__ tileLB, uint32_t *__restrict__ cell_near,
+                 unsigned int *__restrict__ n_with_tiles) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(sort_smem) + static_cast<size_t>(warp) * SORT_MAX;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned int with_tiles = 0;
     for (uint32_t code = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; code < ncodes; code += nwarps) {
         const uint32_t n = cell_cnt[code];
         if (n == 0) { if (lane == 0) cell_near[code] = 0; continue; }
+        ++with_tiles;
         const uint32_t off = cell_start[code];
         uint32_t near = 0;
         if (n <= SORT_MAX) {
@@ -219,6 +222,7 @@ tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__rest
         if (n - near > 0xFFFFFFu) near = n;          // the far length must fit the 24 bits of a work item
         if (lane == 0) cell_near[code] = near;
     }
+    if (lane == 0 && with_tiles) atomicAdd(n_with_tiles, with_tiles);
 }
 
 // tile lengths rounded up to 4 entries so every tile starts 16-byte aligned in all three pool arrays
@@ -284,6 +288,20 @@ __device__ __forceinline__ Tri tri_of_count(uint32_t cnt) {
 }
 
 // phase A: per-block totals
+// A voxel's counter may be split into `nsub` sub-cells (dense clouds: the atomics of one voxel spread over several
+// addresses); the voxel's count is their sum, its run is the concatenation of the sub-runs.
+template <int NSUB>
+__device__ __forceinline__ uint32_t voxel_count(const uint32_t *count, int stride, uint32_t code) {
+    uint32_t c[NSUB];
+#pragma unroll
+    for (int sidx = 0; sidx < NSUB; ++sidx) c[sidx] = count[(static_cast<size_t>(code) * NSUB + sidx) * stride];   // loads in flight together
+    uint32_t sum = 0;
+#pragma unroll
+    for (int sidx = 0; sidx < NSUB; ++sidx) sum += c[sidx];
+    return sum;
+}
+
+template <int NSUB>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ count, int stride, uint32_t ncodes,
                                                                    Tri *__restrict__ block_sums) {
     __shared__ Tri total;
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_
     Tri v{0, 0, 0};
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < ncodes) v = tri_add(v, tri_of_count(count[static_cast<size_t>(base + i) * stride]));
+        if (base + i < ncodes) v = tri_add(v, tri_of_count(voxel_count<NSUB>(count, stride, base + i)));
     block_exclusive_scan(v, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
@@ -326,6 +344,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(Tri *__restri
 // atomicAdd returns both the run start and the slot inside the run.
 // mode 1 (points): start[code] = first sorted point of the voxel, and the voxel's work items
 // {tile offset, near length, first point, point count <= 64 | far length << 8} are emitted in voxel-id order.
+template <int NSUB>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *count, int stride, uint32_t ncodes,
                                                                   const Tri *__restrict__ block_sums, int mode,
                                                                   uint32_t *start,
@@ -333,28 +352,57 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
                                                                   const uint32_t *__restrict__ tile_cnt,
                                                                   const uint32_t *__restrict__ tile_near,
                                                                   uint4 *__restrict__ items) {
+    const int lane = threadIdx.x & 31;
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     uint32_t cnt[SCAN_ITEMS];
     Tri v{0, 0, 0};
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        cnt[i] = (base + i < ncodes) ? count[static_cast<size_t>(base + i) * stride] : 0u;
+        cnt[i] = (base + i < ncodes) ? voxel_count<NSUB>(count, stride, base + i) : 0u;
         v = tri_add(v, tri_of_count(cnt[i]));
     }
     Tri run = tri_add(block_exclusive_scan(v, nullptr), block_sums[blockIdx.x]);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
+        uint32_t toff = 0, tnear = 0, far = 0, n_items = 0;
         if (base + i < ncodes) {
-            if (mode == 0) start[base + i] = run.a;
-            else *reinterpret_cast<uint2 *>(start + 2 * CELL_PAD * static_cast<size_t>(base + i)) = make_uint2(0u, run.a);
-            if (mode == 1 && cnt[i]) {
-                const uint32_t toff = tile_start[base + i], tcnt = tile_cnt[base + i], tnear = tile_near[base + i];
-                const uint32_t far = tcnt - tnear;                       // < 2^24 (tile_sort_kernel)
-                const uint32_t n_items = (cnt[i] + PTS_PER_ITEM - 1) / PTS_PER_ITEM;
-                for (uint32_t t = 0; t < n_items; ++t)
-                    items[run.c + t] = make_uint4(toff, tnear, run.a + t * PTS_PER_ITEM,
-                                                  min(static_cast<uint32_t>(PTS_PER_ITEM), cnt[i] - t * PTS_PER_ITEM) | (far << 8));
+            if (mode == 0) {
+                start[base + i] = run.a;
+            } else {
+                uint32_t c[NSUB];
+#pragma unroll
+                for (int sidx = 0; sidx < NSUB; ++sidx) c[sidx] = count[(static_cast<size_t>(base + i) * NSUB + sidx) * stride];
+                uint32_t sub_start = run.a;
+#pragma unroll
+                for (int sidx = 0; sidx < NSUB; ++sidx) {
+                    *reinterpret_cast<uint2 *>(start + (static_cast<size_t>(base + i) * NSUB + sidx) * stride) = make_uint2(0u, sub_start);
+                    sub_start += c[sidx];
+                }
+                if (cnt[i]) {
+                    toff = tile_start[base + i];
+                    tnear = tile_near[base + i];
+                    far = tile_cnt[base + i] - tnear;                // < 2^24 (tile_sort_kernel)
+                    n_items = (cnt[i] + PTS_PER_ITEM - 1) / PTS_PER_ITEM;
+                }
             }
+        }
+        // work items of the voxel: a few -> this thread; a crowded voxel (dense clouds: hundreds of items) -> the whole
+        // warp, so that no thread ends up writing thousands of items alone
+        if (n_items && n_items <= 4)
+            for (uint32_t t = 0; t < n_items; ++t)
+                items[run.c + t] = make_uint4(toff, tnear, run.a + t * PTS_PER_ITEM,
+                                              min(static_cast<uint32_t>(PTS_PER_ITEM), cnt[i] - t * PTS_PER_ITEM) | (far << 8));
+        uint32_t crowded = __ballot_sync(0xffffffffu, n_items > 4);
+        while (crowded) {
+            const int src = __ffs(crowded) - 1;
+            crowded &= crowded - 1;
+            const uint32_t s_toff = __shfl_sync(0xffffffffu, toff, src), s_near = __shfl_sync(0xffffffffu, tnear, src),
+                           s_far = __shfl_sync(0xffffffffu, far, src), s_first = __shfl_sync(0xffffffffu, run.c, src),
+                           s_pt = __shfl_sync(0xffffffffu, run.a, src), s_cnt = __shfl_sync(0xffffffffu, cnt[i], src);
+            const uint32_t s_items = (s_cnt + PTS_PER_ITEM - 1) / PTS_PER_ITEM;
+            for (uint32_t t = lane; t < s_items; t += 32)
+                items[s_first + t] = make_uint4(s_toff, s_near, s_pt + t * PTS_PER_ITEM,
+                                                min(static_cast<uint32_t>(PTS_PER_ITEM), s_cnt - t * PTS_PER_ITEM) | (s_far << 8));
         }
         run = tri_add(run, tri_of_count(cnt[i]));
     }
@@ -362,14 +410,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 }
 
 static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mode, uint32_t *start, const uint32_t *tile_start,
-                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, DevStats *st, cudaStream_t stream) {
+                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, DevStats *st, cudaStream_t stream, int nsub = 1) {
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
     Tri *bs = h->block_sums.as<Tri>();
     const int stride = mode == 1 ? 2 * CELL_PAD : 1;
-    scan_reduce_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);
-    scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);
-    scan_apply_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs, mode, start, tile_start, tile_cnt, tile_near, items);
+#define TM_SCAN_CASE(S)                                                                                                        \
+    do {                                                                                                                       \
+        scan_reduce_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);                                \
+        scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);                                                   \
+        scan_apply_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs, mode, start, tile_start, tile_cnt, \
+                                                                   tile_near, items);                                          \
+    } while (0)
+    switch (nsub) {
+        case 2: TM_SCAN_CASE(2); break;
+        case 4: TM_SCAN_CASE(4); break;
+        case 8: TM_SCAN_CASE(8); break;
+        default: TM_SCAN_CASE(1); break;
+    }
+#undef TM_SCAN_CASE
     TM_CUDA(h, cudaGetLastError());
     return TM_OK;
 }
@@ -512,15 +571,19 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
                                                     h->boxhi.as<float4>(), m, g, 1, counter, h->cyl_cell_start.as<uint32_t>(),
                                                     h->tile_keys.as<unsigned long long>(), h->long_list.as<int32_t>(), d_nlong);
     TM_KCHECK(h, stream, "cyl_register_kernel (fill)");
+    TM_CUDA(h, cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), stream));      // reused as the "voxels with a tile" counter
     const size_t sort_smem = sizeof(unsigned long long) * SORT_MAX * SORT_WARPS;
     TM_CUDA(h, cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sort_smem)));
     const int sort_blocks = static_cast<int>(std::min<uint32_t>((ncodes + SORT_WARPS - 1) / SORT_WARPS, static_cast<uint32_t>(h->sm_count) * 3));
     tile_sort_kernel<<<sort_blocks, SORT_WARPS * 32, sort_smem, stream>>>(
         h->cyl_cell_start.as<uint32_t>(), h->cyl_cell_cnt.as<uint32_t>(), ncodes, h->tile_keys.as<unsigned long long>(),
         h->recA.as<float4>(), h->recB.as<float4>(), h->near, h->tileA.as<float4>(), h->tileB.as<float4>(),
-        h->tileI.as<int32_t>(), h->tileLB.as<float>(), h->cyl_cell_near.as<uint32_t>());
+        h->tileI.as<int32_t>(), h->tileLB.as<float>(), h->cyl_cell_near.as<uint32_t>(), d_nlong);
     TM_KCHECK(h, stream, "tile_sort_kernel");
+    unsigned int with_tiles = 0;
+    TM_CUDA(h, cudaMemcpyAsync(&with_tiles, d_nlong, sizeof(with_tiles), cudaMemcpyDeviceToHost, stream));
     TM_CUDA(h, cudaStreamSynchronize(stream));
+    h->voxels_with_tiles = with_tiles;
     h->tile_keys.release();                 // build-time only
     rc = build_bvh(h, stream);
     if (rc != TM_OK) return rc;
@@ -548,7 +611,7 @@ __device__ __forceinline__ uint32_t point_code(const GridDev &g, float x, float 
 // that issues ONE atomic for the group.  A randomly ordered cloud gains nothing (no two lanes share a voxel, the match
 // costs a few instructions next to an L2 atomic); a spatially coherent one — tiled exports, scan lines, re-labelling a
 // sorted cloud — sends up to 32x fewer atomics.
-__global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
+__global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub,
                                                         uint2 *__restrict__ cells, int32_t *__restrict__ pend_idx,
                                                         unsigned long long *__restrict__ pend_keys,
                                                         uint32_t *__restrict__ brute_slots, DevStats *__restrict__ st) {
@@ -575,13 +638,15 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
             }
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, code);
-        if (valid && lane == __ffs(peers) - 1) atomicAdd(&cells[static_cast<size_t>(code) * CELL_PAD].x, static_cast<uint32_t>(__popc(peers)));
+        // the warp's sub-cell: a function of the row index only, so that the scatter pass finds the same one
+        const size_t cell = (static_cast<size_t>(code) * nsub + (static_cast<uint32_t>(base >> 5) & (nsub - 1))) * CELL_PAD;
+        if (valid && lane == __ffs(peers) - 1) atomicAdd(&cells[cell].x, static_cast<uint32_t>(__popc(peers)));
     }
 }
 
 // pass 2: each point takes the next free slot of its voxel's run.  A cell is {cursor, run start}: one 64-bit atomic per
 // group of lanes advances the cursor by the group size and returns both words.
-__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g,
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub,
                                                           uint2 *__restrict__ cells, float4 *__restrict__ sorted) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -601,7 +666,9 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
         const int leader = __ffs(peers) - 1;
         unsigned long long cell = 0;
         if (valid && lane == leader)
-            cell = atomicAdd(reinterpret_cast<unsigned long long *>(cells + static_cast<size_t>(code) * CELL_PAD), static_cast<unsigned long long>(__popc(peers)));
+            cell = atomicAdd(reinterpret_cast<unsigned long long *>(
+                                 cells + (static_cast<size_t>(code) * nsub + (static_cast<uint32_t>(base >> 5) & (nsub - 1))) * CELL_PAD),
+                             static_cast<unsigned long long>(__popc(peers)));
         cell = __shfl_sync(0xffffffffu, cell, leader);
         if (valid) {
             const uint32_t pos = static_cast<uint32_t>(cell >> 32) + static_cast<uint32_t>(cell) + static_cast<uint32_t>(__popc(peers & lt));
@@ -1092,7 +1159,15 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     // scratch
     const size_t max_occ = std::min<size_t>(n, ncodes);
     const size_t max_items = n / PTS_PER_ITEM + max_occ + 1;
-    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * CELL_PAD * (static_cast<size_t>(ncodes) + 1)));
+    // dense clouds (hundreds of points per voxel) queue their atomics on the voxels' counters: split each counter into
+    // 2 / 4 / 8 sub-cells.  The density is judged by the voxels that have a tile at all (known per table).
+    int nsub = 1;
+    {
+        const double density = static_cast<double>(n) / std::max<uint32_t>(1u, h->voxels_with_tiles);
+        if (density > 640.0) nsub = 8; else if (density > 320.0) nsub = 4; else if (density > 160.0) nsub = 2;
+        if (const char *env = getenv("TM_SUBCELLS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) nsub = v; }
+    }
+    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * CELL_PAD * nsub * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
     TM_CUDA(h, h->items.ensure(sizeof(uint4) * max_items));
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
@@ -1105,20 +1180,20 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
-    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * CELL_PAD * ncodes, st));
+    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * CELL_PAD * nsub * ncodes, st));
 
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
-    bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cells.as<uint2>(),
+    bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, h->cells.as<uint2>(),
                                                 h->pend_idx.as<int32_t>(), h->keys.as<unsigned long long>(),
                                                 h->brute_slots.as<uint32_t>(), dst);
     TM_KCHECK(h, st, "bin_count_kernel");
     mark(h, 1, st);
     int rc = run_scan(h, h->cells.as<uint32_t>(), ncodes, 1, h->cells.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
-                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), dst, st);
+                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), dst, st, nsub);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
     mark(h, 2, st);
-    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, h->cells.as<uint2>(), h->sorted_pts.as<float4>());
+    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, h->cells.as<uint2>(), h->sorted_pts.as<float4>());
     TM_KCHECK(h, st, "bin_scatter_kernel");
 
     mark(h, 3, st);
