@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[1], [3], [4] and the small-table caller on ONE B200 (bench.py measures configs[2]).
 
-    python scripts/bench_configs.py --out gpurun_out/configs.json [--max-points 100000000] [--skip-sweep]
+    python tests/bench_configs.py --out gpurun_out/configs.json [--max-points 100000000] [--skip-sweep]
 
 config 1 : single tree, 100k points x 2k cylinders (the reference's own CPU-runnable case): device resident, through the
            LabelGenerationCuda drop-in, and the oracle port on the host cores; all 100k rows compared bit-for-bit.
@@ -15,6 +15,8 @@ config 5 : sweep N in {1e5, 1e6, 1e7, 1e8} x M in {1e3, 1e4, 5e4, 2e5}, device r
            the test-suite) and against the oracle on a smaller one.
 small    : cylinder_proximity_based_segmentation call pattern (M = 5, n = 2k / 50k rows of a resident 1M cloud):
            calls per second through tm_proximity_flags_host.
+
+Lives under tests/ because it uses the CPU oracle as its checker (only tests/, smoke() and bench.py's CPU legs may).
 
 Timing: CUDA events, 3 warm-up + 5 timed repetitions, L2 flushed (256 MiB write) between repetitions; host paths by
 wall clock around synchronous calls.  Not part of the driver's contract; results are committed under profiles/.
