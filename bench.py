@@ -38,8 +38,8 @@ UNIT = "points/s"
 OPS_PER_PAIR = 81                 # fp32 lane-ops per evaluated pair in reference order
 BYTES_PER_POINT = 36              # compulsory HBM traffic per point: 12 B xyz in + 24 B index/id/dist/offset out
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-call kernel, from the committed ncu --set full capture
-# of THIS command at the default workload (profiles/r01f_grid_kernels.md); null for any other workload
-NCU_DRAM_BYTES = {"evaluate": 345.46e6, "bin": 127.13e6, "scatter": 276.80e6, "epilogue": 316.56e6, "tree": 7.93e6}
+# of THIS command at the default workload (profiles/r01h_grid_kernels.md); null for any other workload
+NCU_DRAM_BYTES = {"evaluate": 346.81e6, "bin": 128.54e6, "scatter": 281.17e6, "epilogue": 314.56e6, "tree": 7.93e6}
 
 
 def load_peaks():
@@ -359,7 +359,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak,
                 "traffic": NCU_DRAM_BYTES.get(dom) if (N_POINTS, N_CYLINDERS) == (10_000_000, 50_000) and args.mode == "grid" else None,
-                "traffic_source": "profiles/r01f_grid_kernels.md (ncu --set full, bytes per launch)", "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "traffic_source": "profiles/r01h_grid_kernels.md (ncu --set full, bytes per launch)", "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "kernel_ms": dom_ms,
                 "note": "dominant kernel is FP32-issue bound, not HBM bound: see fp32_roofline"}
     fp32_roofline = {"kernel": dom, "pairs_evaluated": pairs, "lane_ops_per_pair": OPS_PER_PAIR,
