@@ -322,6 +322,7 @@ int tm_destroy(tm_handle *h) {
     }
     if (h->small_stream) cudaStreamDestroy(h->small_stream);
     delete h->pool;
+    if (h->bvh_pinned) cudaFreeHost(h->bvh_pinned);
     for (auto &b : h->chunk_packed) b.release();
     for (auto &s : h->pipe_stream) if (s) cudaStreamDestroy(s);
     for (auto &e : h->pipe_event) if (e) cudaEventDestroy(e);

@@ -49,15 +49,16 @@ static inline uint32_t expand10(uint32_t v) {
 }
 
 struct BuildCtx {
-    const std::vector<float4> *lo, *hi;
-    const std::vector<int32_t> *order;
-    std::vector<BvhNode> nodes;
+    const float4 *lo, *hi;
+    const int32_t *order;
+    BvhNode *nodes;          // pinned staging
+    int n_nodes;
 };
 
 static void box_of(const BuildCtx &cx, int first, int count, float *lo, float *hi) {
     for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
     for (int i = first; i < first + count; ++i) {
-        const float4 a = (*cx.lo)[(*cx.order)[i]], b = (*cx.hi)[(*cx.order)[i]];
+        const float4 a = cx.lo[cx.order[i]], b = cx.hi[cx.order[i]];
         lo[0] = std::min(lo[0], a.x); lo[1] = std::min(lo[1], a.y); lo[2] = std::min(lo[2], a.z);
         hi[0] = std::max(hi[0], b.x); hi[1] = std::max(hi[1], b.y); hi[2] = std::max(hi[2], b.z);
     }
@@ -69,8 +70,7 @@ static int32_t build_range(BuildCtx &cx, int first, int count, float *lo, float 
         box_of(cx, first, count, lo, hi);
         return -1 - ((first << 3) | (count - 1));
     }
-    const int id = static_cast<int>(cx.nodes.size());
-    cx.nodes.emplace_back();
+    const int id = cx.n_nodes++;
     const int half = count / 2;
     float l0[3], h0[3], l1[3], h1[3];
     const int32_t c0 = build_range(cx, first, half, l0, h0);
@@ -99,21 +99,33 @@ int build_bvh(tm_handle *h, cudaStream_t stream) {
     h->bvh_count = 0;
     h->bvh_root = 0;
     if (m > (1 << 27)) return fail(h, TM_ERR_INVALID, "tm_set_cylinders: more than 2^27 cylinders%s%s");
-    std::vector<float4> lo(m), hi(m);
-    TM_CUDA(h, cudaMemcpyAsync(lo.data(), h->boxlo.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
-    TM_CUDA(h, cudaMemcpyAsync(hi.data(), h->boxhi.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
+    // pinned staging (grow-only, owned by the handle): pageable copies of a few MB cost more than the build itself
+    const size_t box_bytes = sizeof(float4) * 2 * static_cast<size_t>(m);
+    const size_t out_bytes = sizeof(BvhNode) * (static_cast<size_t>(m) / 2 + 2) + sizeof(int32_t) * static_cast<size_t>(m);
+    if (h->bvh_pinned_cap < box_bytes + out_bytes) {
+        if (h->bvh_pinned) cudaFreeHost(h->bvh_pinned);
+        h->bvh_pinned = nullptr;
+        h->bvh_pinned_cap = 0;
+        TM_CUDA(h, cudaMallocHost(&h->bvh_pinned, box_bytes + out_bytes + (1 << 16)));
+        h->bvh_pinned_cap = box_bytes + out_bytes + (1 << 16);
+    }
+    float4 *lo_p = static_cast<float4 *>(h->bvh_pinned), *hi_p = lo_p + m;
+    TM_CUDA(h, cudaMemcpyAsync(lo_p, h->boxlo.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
+    TM_CUDA(h, cudaMemcpyAsync(hi_p, h->boxhi.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
     TM_CUDA(h, cudaStreamSynchronize(stream));
-    std::vector<int32_t> order;
-    order.reserve(m);
+    struct Span { const float4 *p; const float4 &operator[](size_t i) const { return p[i]; } };
+    const Span lo{lo_p}, hi{hi_p};
+    BvhNode *nodes_p = reinterpret_cast<BvhNode *>(hi_p + m);
+    int32_t *order = reinterpret_cast<int32_t *>(nodes_p + (static_cast<size_t>(m) / 2 + 2));
+    int n = 0;
     float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int c = 0; c < m; ++c) {
         if (!(lo[c].w == 0.f)) continue;                  // special cylinders are not in the tree
-        order.push_back(c);
+        order[n++] = c;
         const float cx = 0.5f * (lo[c].x + hi[c].x), cy = 0.5f * (lo[c].y + hi[c].y), cz = 0.5f * (lo[c].z + hi[c].z);
         clo[0] = std::min(clo[0], cx); clo[1] = std::min(clo[1], cy); clo[2] = std::min(clo[2], cz);
         chi[0] = std::max(chi[0], cx); chi[1] = std::max(chi[1], cy); chi[2] = std::max(chi[2], cz);
     }
-    const int n = static_cast<int>(order.size());
     if (n == 0) return TM_OK;
     std::vector<uint64_t> keyed(n);
     float scale[3];
@@ -126,25 +138,38 @@ int build_bvh(tm_handle *h, cudaStream_t stream) {
         const uint32_t code = expand10(qx) | (expand10(qy) << 1) | (expand10(qz) << 2);
         keyed[i] = (static_cast<uint64_t>(code) << 32) | static_cast<uint32_t>(c);
     }
-    std::sort(keyed.begin(), keyed.end());
+    // LSD radix sort of the 30-bit codes, 3 passes of 10 bits (stable: ties keep ascending rows); std::sort costs 3 ms at 50k
+    {
+        std::vector<uint64_t> tmp(n);
+        uint64_t *src = keyed.data(), *dst = tmp.data();
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = 32 + 10 * pass;
+            uint32_t hist[1025] = {0};
+            for (int i = 0; i < n; ++i) ++hist[((src[i] >> shift) & 1023u) + 1];
+            for (int b = 0; b < 1024; ++b) hist[b + 1] += hist[b];
+            for (int i = 0; i < n; ++i) dst[hist[(src[i] >> shift) & 1023u]++] = src[i];
+            std::swap(src, dst);
+        }
+        if (src != keyed.data()) std::memcpy(keyed.data(), src, sizeof(uint64_t) * n);
+    }
     for (int i = 0; i < n; ++i) order[i] = static_cast<int32_t>(static_cast<uint32_t>(keyed[i]));
     BuildCtx cx;
-    cx.lo = &lo; cx.hi = &hi; cx.order = &order;
-    cx.nodes.reserve(static_cast<size_t>(n) / 2 + 2);
+    cx.lo = lo_p; cx.hi = hi_p; cx.order = order;
+    cx.nodes = nodes_p; cx.n_nodes = 0;
     float rlo[3], rhi[3];
     h->bvh_root = build_range(cx, 0, n, rlo, rhi);
     h->bvh_count = n;
-    const size_t nnodes = std::max<size_t>(cx.nodes.size(), 1);
+    const size_t nnodes = std::max<size_t>(static_cast<size_t>(cx.n_nodes), 1);
     TM_CUDA(h, h->bvh_nodes.ensure(sizeof(BvhNode) * nnodes));
     TM_CUDA(h, h->bvh_rows.ensure(sizeof(int32_t) * n));
     TM_CUDA(h, h->bvh_leafAB.ensure(sizeof(float4) * 2 * n));
-    if (!cx.nodes.empty())
-        TM_CUDA(h, cudaMemcpyAsync(h->bvh_nodes.p, cx.nodes.data(), sizeof(BvhNode) * cx.nodes.size(), cudaMemcpyHostToDevice, stream));
-    TM_CUDA(h, cudaMemcpyAsync(h->bvh_rows.p, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+    if (cx.n_nodes > 0)
+        TM_CUDA(h, cudaMemcpyAsync(h->bvh_nodes.p, nodes_p, sizeof(BvhNode) * cx.n_nodes, cudaMemcpyHostToDevice, stream));
+    TM_CUDA(h, cudaMemcpyAsync(h->bvh_rows.p, order, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
     bvh_leaf_gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(h->bvh_rows.as<int32_t>(), n, h->recAB.as<float4>(),
                                                               h->bvh_leafAB.as<float4>());
     TM_KCHECK(h, stream, "bvh_leaf_gather_kernel");
-    TM_CUDA(h, cudaStreamSynchronize(stream));            // the host vectors go out of scope
+    TM_CUDA(h, cudaStreamSynchronize(stream));            // the staging buffer is reused by the next build
     return TM_OK;
 }
 

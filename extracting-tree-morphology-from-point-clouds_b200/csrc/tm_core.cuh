@@ -101,6 +101,8 @@ struct tm_handle {
     tmn::DevBuf bvh_rows;            // int32: cylinder row per leaf slot (Morton order)
     tmn::DevBuf bvh_leafAB;          // float4[2 x count]: records in leaf order
     int32_t bvh_root = 0, bvh_count = 0;
+    void *bvh_pinned = nullptr;      // host staging of the BVH build
+    size_t bvh_pinned_cap = 0;
     uint64_t index_entries = 0;
     uint32_t voxels_with_tiles = 0;  // voxels within D_max of some cylinder (density estimate for the point sort)
 

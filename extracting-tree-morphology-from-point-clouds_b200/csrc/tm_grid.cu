@@ -33,6 +33,7 @@
 // on-axis-line test in variant A (NaN wins the argmin at any distance).
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
 
 #include "tm_core.cuh"
@@ -470,6 +471,14 @@ static inline float slack_floor_for(float h) { return std::min(1e-4f, 4e-4f * h)
 static inline float slack_for(float maxabs, float h) { return slack_floor_for(h) + 4e-6f * maxabs; }
 
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
+    static const bool trace_build = [] { const char *e = getenv("TM_TRACE_BUILD"); return e && e[0] == '1'; }();
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace_build) return;
+        cudaStreamSynchronize(stream);
+        fprintf(stderr, "[tm build] %-22s %8.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     // global bounding box of the regular cylinders' AABBs (written by pack_kernel as ordered ints)
     int host_box[10];
     TM_CUDA(h, cudaMemcpyAsync(host_box, h->bbox.p, sizeof(host_box), cudaMemcpyDeviceToHost, stream));
@@ -545,6 +554,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
                                                     h->boxhi.as<float4>(), m, g, 0, counter, nullptr, nullptr,
                                                     h->long_list.as<int32_t>(), d_nlong);
     TM_KCHECK(h, stream, "cyl_register_kernel (count)");
+    lap("register (count)");
     align4_kernel<<<(ncodes + 255) / 256, 256, 0, stream>>>(counter, h->cyl_cell_cnt.as<uint32_t>(), rounded, ncodes);
     int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc != TM_OK) return rc;
@@ -552,6 +562,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_CUDA(h, cudaMemcpyAsync(&total, h->cyl_cell_start.as<uint32_t>() + ncodes, 4, cudaMemcpyDeviceToHost, stream));
     TM_CUDA(h, cudaMemcpyAsync(&nlong, d_nlong, 4, cudaMemcpyDeviceToHost, stream));
     TM_CUDA(h, cudaStreamSynchronize(stream));
+    lap("scan + sizes");
     h->n_long = nlong;
     h->index_entries = total;
     h->n_listed = n_regular - nlong;
@@ -571,6 +582,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
                                                     h->boxhi.as<float4>(), m, g, 1, counter, h->cyl_cell_start.as<uint32_t>(),
                                                     h->tile_keys.as<unsigned long long>(), h->long_list.as<int32_t>(), d_nlong);
     TM_KCHECK(h, stream, "cyl_register_kernel (fill)");
+    lap("alloc + register (fill)");
     TM_CUDA(h, cudaMemsetAsync(d_nlong, 0, sizeof(unsigned int), stream));      // reused as the "voxels with a tile" counter
     const size_t sort_smem = sizeof(unsigned long long) * SORT_MAX * SORT_WARPS;
     TM_CUDA(h, cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sort_smem)));
@@ -584,9 +596,11 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_CUDA(h, cudaMemcpyAsync(&with_tiles, d_nlong, sizeof(with_tiles), cudaMemcpyDeviceToHost, stream));
     TM_CUDA(h, cudaStreamSynchronize(stream));
     h->voxels_with_tiles = with_tiles;
-    h->tile_keys.release();                 // build-time only
+    lap("tile sort");
+    // (tile_keys is build-time scratch, kept for the next table: cudaFree + cudaMalloc cost more than the build's kernels)
     rc = build_bvh(h, stream);
     if (rc != TM_OK) return rc;
+    lap("bvh (host)");
     h->have_grid = true;
     return TM_OK;
 }
