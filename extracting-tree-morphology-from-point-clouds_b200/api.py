@@ -14,6 +14,7 @@ argument conventions for the hot path:
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -196,7 +197,7 @@ class Engine:
             cloud = np.ascontiguousarray(cloud)
         n = cloud.shape[0]
         if out is None:
-            out = np.empty((n, 7), dtype=np.float64)
+            out = self._new_records(n)
         if out.shape != (n, 7) or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float64 (N,7) array")
         dist = np.empty(n, dtype=np.float32) if want_dist else None
@@ -206,6 +207,19 @@ class Engine:
             self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride,
             ctypes.byref(prm), out.ctypes.data, dist.ctypes.data if dist is not None else None))
         return (out, dist) if want_dist else out
+
+    @staticmethod
+    def _new_records(n: int) -> np.ndarray:
+        """The (N,7) float64 result array.  TM_PINNED_OUT=1 makes it page-locked (torch's caching host allocator, so
+        repeated calls reuse the block; arrays above TM_PINNED_OUT_MAX_MB, default 4096, stay pageable): no first-touch page
+        faults, ~10 % off a 10M-point call, at the price of memory that stays locked in torch's cache."""
+        nbytes = n * 56
+        if n > 0 and os.environ.get("TM_PINNED_OUT", "0") == "1" and nbytes <= int(os.environ.get("TM_PINNED_OUT_MAX_MB", "4096")) << 20:
+            try:
+                return torch.empty((n, 7), dtype=torch.float64, pin_memory=True).numpy()
+            except RuntimeError:
+                pass
+        return np.empty((n, 7), dtype=np.float64)
 
     # -- small-table fast path (QSMFittingDepthFirst.py:1006-1094) ---------------------------------
     def upload_cloud(self, cloud: np.ndarray) -> None:

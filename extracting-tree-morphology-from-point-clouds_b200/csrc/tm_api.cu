@@ -8,6 +8,7 @@
 #include <functional>
 #include <mutex>
 #include <new>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -561,6 +562,13 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     const size_t in_bytes = static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
     const size_t pk_bytes = static_cast<size_t>(chunk) * sizeof(float4);
     const size_t out_bytes = pk_bytes + static_cast<size_t>(chunk) * sizeof(float);
+    // A pinned record array can also be written by the copy engine: TM_HOST_SPLIT=1..100 percent of the chunks are
+    // assembled on the device and DMA'd straight into the caller's rows (56 B/point over PCIe) while the host workers
+    // assemble the others (16 B/point).  Off by default: on the hosts measured (profiles/r01i_host_pipeline.md) the
+    // record array's DRAM write bandwidth is the limit either way, and the two writers only get in each other's way.
+    int split = 0;
+    if (const char *env = getenv("TM_HOST_SPLIT")) { if (host_is_pinned(out_records_host)) split = std::max(0, std::min(100, atoi(env))); }
+    auto on_device = [split](int64_t c) { return ((c + 1) * split) / 100 > (c * split) / 100; };
     for (int b = 0; b < 2; ++b) {
         if (!in_pinned && h->pinned_in_cap < in_bytes) {
             if (h->pinned_in[b]) { cudaFreeHost(h->pinned_in[b]); h->pinned_in[b] = nullptr; }
@@ -573,28 +581,45 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
         TM_CUDA(h, h->chunk_in[b].ensure(in_bytes + (dtype == TM_F64 ? static_cast<size_t>(chunk) * 12 : 0)));
         TM_CUDA(h, h->chunk_packed[b].ensure(pk_bytes));
         TM_CUDA(h, h->chunk_dist[b].ensure(static_cast<size_t>(chunk) * 4));
+        if (split) {
+            TM_CUDA(h, h->chunk_rec[b].ensure(static_cast<size_t>(chunk) * 7 * sizeof(double)));
+            TM_CUDA(h, h->chunk_off[b].ensure(static_cast<size_t>(chunk) * 12));
+            TM_CUDA(h, h->chunk_id[b].ensure(static_cast<size_t>(chunk) * 4));
+        }
     }
     if (!in_pinned) h->pinned_in_cap = std::max(h->pinned_in_cap, in_bytes);
     h->pinned_out_cap = std::max(h->pinned_out_cap, out_bytes);
 
     // events: [0,1] H2D done per buffer, [2,3] compute done, [4,5] D2H done
     tm_stats total{};
+    size_t d2h_total = 0;
+    const bool trace = getenv("TM_TRACE_HOST") != nullptr;
+    double t_issue = 0, t_wait = 0, t_asm = 0, t_stage = 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    std::vector<cudaEvent_t> tev;                       // trace only: [4c] H2D start, [4c+1] H2D end, [4c+2] label end, [4c+3] D2H end
+    auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const unsigned char *src = static_cast<const unsigned char *>(cloud_host);
     auto assemble = [&](int64_t c) -> int {
         const int b = static_cast<int>(c & 1);
         const int64_t cnt = std::min(chunk, n - c * chunk);
+        const double w0 = now();
         TM_CUDA(h, cudaEventSynchronize(h->pipe_event[4 + b]));
-        const float4 *packed = static_cast<const float4 *>(h->pinned_out[b]);
-        const unsigned char *crow = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
-        double *orow = out_records_host + c * chunk * 7;
-        h->pool->run([=](unsigned t, unsigned nt) {
-            const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
-            if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1);
-            else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1);
-        });
+        const double w1 = now();
+        t_wait += w1 - w0;
+        if (!on_device(c)) {
+            const float4 *packed = static_cast<const float4 *>(h->pinned_out[b]);
+            const unsigned char *crow = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+            double *orow = out_records_host + c * chunk * 7;
+            h->pool->run([=](unsigned t, unsigned nt) {
+                const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
+                if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1);
+                else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1);
+            });
+        }
         if (out_dist_host)
             memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b]) + pk_bytes, static_cast<size_t>(cnt) * sizeof(float));
+        t_asm += now() - w1;
         return TM_OK;
     };
     int rc = TM_OK;
@@ -604,12 +629,18 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
         const size_t bytes = static_cast<size_t>(cnt) * static_cast<size_t>(row_stride) * esz;
         const unsigned char *csrc = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
         // buffers b were last used by chunk c-2, which was assembled (hence fully transferred) in iteration c-1
+        const double i0 = now();
         if (!in_pinned) {
             par_memcpy(h->pinned_in[b], csrc, bytes);
+            t_stage += now() - i0;
+        }
+        tmark(s_in);
+        if (!in_pinned) {
             TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b], bytes, cudaMemcpyHostToDevice, s_in));
         } else {
             TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
         }
+        tmark(s_in);
         TM_CUDA(h, cudaEventRecord(h->pipe_event[0 + b], s_in));
         TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[0 + b], 0));
         const float *pts32;
@@ -626,22 +657,38 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
             stride32 = row_stride;
         }
         h->stats = tm_stats{};
-        LabelArgs a{pts32, cnt, stride32, *params, nullptr, nullptr, out_dist_host ? h->chunk_dist[b].as<float>() : nullptr,
-                    nullptr, nullptr, s_cmp};
-        a.out_packed = h->chunk_packed[b].as<float4>();
+        const bool dev = on_device(c);
+        LabelArgs a{pts32, cnt, stride32, *params, nullptr, dev ? h->chunk_id[b].as<int32_t>() : nullptr,
+                    out_dist_host ? h->chunk_dist[b].as<float>() : nullptr, dev ? h->chunk_off[b].as<float>() : nullptr, nullptr, s_cmp};
+        if (!dev) a.out_packed = h->chunk_packed[b].as<float4>();
         rc = label_dispatch(h, a);
         if (rc != TM_OK) return rc;
         total.pairs_evaluated += h->stats.pairs_evaluated;
         total.points_brute += h->stats.points_brute;
         h->last_n = cnt;
+        if (dev) {
+            rc = tm_assemble_records(h, h->chunk_in[b].p, dtype, cnt, row_stride, h->chunk_off[b].as<float>(),
+                                     h->chunk_id[b].as<int32_t>(), h->chunk_rec[b].as<double>(), s_cmp);
+            if (rc != TM_OK) return rc;
+        }
+        tmark(s_cmp);
         TM_CUDA(h, cudaEventRecord(h->pipe_event[2 + b], s_cmp));
         TM_CUDA(h, cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
-        TM_CUDA(h, cudaMemcpyAsync(h->pinned_out[b], h->chunk_packed[b].p, static_cast<size_t>(cnt) * sizeof(float4),
-                                   cudaMemcpyDeviceToHost, s_out));
+        if (dev) {
+            TM_CUDA(h, cudaMemcpyAsync(out_records_host + c * chunk * 7, h->chunk_rec[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double),
+                                       cudaMemcpyDeviceToHost, s_out));
+            d2h_total += static_cast<size_t>(cnt) * 56;
+        } else {
+            TM_CUDA(h, cudaMemcpyAsync(h->pinned_out[b], h->chunk_packed[b].p, static_cast<size_t>(cnt) * sizeof(float4),
+                                       cudaMemcpyDeviceToHost, s_out));
+            d2h_total += static_cast<size_t>(cnt) * 16;
+        }
         if (out_dist_host)
             TM_CUDA(h, cudaMemcpyAsync(static_cast<unsigned char *>(h->pinned_out[b]) + pk_bytes, h->chunk_dist[b].p,
                                        static_cast<size_t>(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        tmark(s_out);
         TM_CUDA(h, cudaEventRecord(h->pipe_event[4 + b], s_out));
+        t_issue += now() - i0;
         if (c >= 1) {
             // the s_cmp work of chunk c must not overwrite chunk_packed / chunk_in of chunk c+1's buffer pair before the
             // transfers of chunk c-1 are done: assembling c-1 here (it waits for its D2H) gives exactly that order
@@ -654,6 +701,21 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     TM_CUDA(h, cudaStreamSynchronize(s_cmp));
     h->stats.pairs_evaluated = total.pairs_evaluated;
     h->stats.points_brute = total.points_brute;
+    if (trace) {
+        float h2d = 0, lab = 0, d2h = 0, span = 0, ms = 0;
+        for (size_t c = 0; c + 3 < tev.size(); c += 4) {
+            cudaEventElapsedTime(&ms, tev[c], tev[c + 1]); h2d += ms;
+            cudaEventElapsedTime(&ms, tev[c + 1], tev[c + 2]); lab += ms;
+            cudaEventElapsedTime(&ms, tev[c + 2], tev[c + 3]); d2h += ms;
+        }
+        if (tev.size() >= 4) cudaEventElapsedTime(&span, tev.front(), tev.back());
+        fprintf(stderr, "[tm host] device side: H2D %.3f ms, H2D end -> label end %.3f, label end -> D2H end %.3f, first H2D -> last D2H %.3f\n", h2d, lab, d2h, span);
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    if (trace)
+        fprintf(stderr, "[tm host] %lld chunks of %lld: issue %.3f ms (of which staging %.3f), wait for D2H %.3f, assemble %.3f\n",
+                static_cast<long long>(nchunks), static_cast<long long>(chunk), t_issue, t_stage, t_wait, t_asm);
+    h->host_d2h_bytes_per_point = static_cast<int32_t>((d2h_total + static_cast<size_t>(n) / 2) / static_cast<size_t>(n)) + (out_dist_host ? 4 : 0);
     return TM_OK;
 }
 

@@ -357,6 +357,21 @@ def test_host_pipeline_variants_agree(eng, f64, monkeypatch):
         assert np.array_equal(rec[:, 6], ora["id"].astype(np.float64))
         assert np.array_equal(dist, ora["dist"], equal_nan=True)
     assert np.array_equal(outs["0"][0], outs["3"][0], equal_nan=True) and np.array_equal(outs["0"][0], outs["16"][0], equal_nan=True)
+    # page-locked record array: some chunks are assembled on the device and written by the copy engine, the others by
+    # the host workers (TM_HOST_SPLIT percent / the rest); every mix gives the same rows
+    monkeypatch.setenv("TM_HOST_ASSEMBLE", "4")
+    for split, per_point in (("0", 20), ("50", 40), ("100", 60), (None, 20)):
+        if split is None:
+            monkeypatch.delenv("TM_HOST_SPLIT")                              # off unless asked for
+        else:
+            monkeypatch.setenv("TM_HOST_SPLIT", split)
+        out = torch.full((len(pts), 7), -1.0, dtype=torch.float64).pin_memory().numpy()
+        rec, dist = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid", want_dist=True, out=out)
+        assert rec is out and abs(eng.host_pipeline_info()["d2h_bytes_per_point"] - per_point) <= 6
+        assert np.array_equal(rec, outs["0"][0], equal_nan=True) and np.array_equal(dist, ora["dist"], equal_nan=True)
+    monkeypatch.setenv("TM_PINNED_OUT", "1")                                 # the engine allocates a page-locked array
+    rec = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid")
+    assert np.array_equal(rec, outs["0"][0], equal_nan=True)
 
 
 def _fuzz_case(rng):
