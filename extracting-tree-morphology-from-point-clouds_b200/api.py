@@ -291,6 +291,34 @@ class Engine:
         self._check(self._lib.tm_radius_count(self._h, _ptr(pts), n, 3, float(radius), _ptr(out), _stream_ptr(self.device)))
         return out
 
+    def noise_cloud(self, cyl_rec: torch.Tensor, first_point: torch.Tensor, n: int | None = None, point0: int = 0, seed: int = 0,
+                    variates=None, want_f32: bool = False):
+        """Rows ``point0 .. point0+n`` of the noisy surface cloud of a QSM (NoiseDataGeneration.py:60-102) → (n,3) float64
+        device tensor (and its float32 rounding with ``want_f32``).  ``cyl_rec`` (M,14) float64 and ``first_point`` (M+1,) int64
+        device tensors as described in ``include/treemorph_nn.h``; ``variates`` = (theta, z, noise) device tensors to replay
+        given draws instead of the Philox stream of ``seed``."""
+        if cyl_rec.dtype != torch.float64 or cyl_rec.dim() != 2 or cyl_rec.shape[1] != 14 or not cyl_rec.is_contiguous():
+            raise ValueError("cyl_rec must be a contiguous (M,14) float64 tensor")
+        m = cyl_rec.shape[0]
+        if first_point.dtype != torch.int64 or first_point.shape != (m + 1,) or not first_point.is_contiguous():
+            raise ValueError("first_point must be a contiguous (M+1,) int64 tensor")
+        if cyl_rec.device != self.device or first_point.device != self.device:
+            raise ValueError(f"cyl_rec / first_point must live on {self.device}")
+        if n is None:
+            n = (int(first_point[-1].item()) if m else 0) - point0
+        out = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        out32 = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_f32 else None
+        th = z = ns = None
+        if variates is not None:
+            th, z, ns = (torch.as_tensor(v, dtype=torch.float64, device=self.device).contiguous() for v in variates)
+            if not (th.shape == z.shape == ns.shape == (n,)):
+                raise ValueError("variates must be three (n,) arrays")
+        self._check(self._lib.tm_noise_cloud(self._h, _ptr(cyl_rec), _ptr(first_point), m, n, int(point0), int(seed) & (2**64 - 1),
+                                             _ptr(th) if th is not None else None, _ptr(z) if z is not None else None,
+                                             _ptr(ns) if ns is not None else None, _ptr(out),
+                                             _ptr(out32) if out32 is not None else None, _stream_ptr(self.device)))
+        return (out, out32) if want_f32 else out
+
     def host_pipeline_info(self) -> dict:
         """D2H bytes per point and host worker threads of the last ``label_cloud_host`` call."""
         b, t = ctypes.c_int32(), ctypes.c_int32()

@@ -13,7 +13,7 @@ from . import build as _build
 TM_OK, TM_ERR_INVALID, TM_ERR_NO_CYLINDERS, TM_ERR_CUDA, TM_ERR_NOMEM, TM_ERR_STATE = range(6)
 TM_MODE_AUTO, TM_MODE_BRUTE, TM_MODE_GRID = 0, 1, 2
 TM_F32, TM_F64 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 TM_PHASES = 9
 PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "tree", "exhaustive", "pending", "epilogue", "total")
 
@@ -59,6 +59,7 @@ SIGNATURES = {
                                                c_f32, c_vp, c_vp, c_vp]),
     "tm_knn_covariance": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "tm_radius_count": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_double, c_vp, c_vp]),
+    "tm_noise_cloud": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tm_host_pipeline_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "tm_get_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(TmStats)]),
     "tm_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TM_ABI_VERSION 4
+#define TM_ABI_VERSION 5
 
 /* status codes */
 #define TM_OK               0
@@ -199,6 +199,26 @@ int tm_knn_covariance(tm_handle *h, const double *pts, int64_t n, int64_t row_st
                       double *out_cov, int32_t *out_idx, void *stream);
 int tm_radius_count(tm_handle *h, const double *pts, int64_t n, int64_t row_stride, double radius,
                     int32_t *out_count, void *stream);
+
+/*
+ * Noisy surface cloud of a QSM on the device (PreProcessing/NoiseDataGeneration.py:60-102; the producer of the clouds
+ * the labelling path consumes).  The per-cylinder part of the reference (:33-58, :77-96: point counts from the
+ * height-dependent density, Rodrigues rotations) is O(M) float64 numpy and stays with the caller, who passes
+ *   cyl_rec      DEVICE (m,14) float64: start xyz, rotation matrix row-major (9), radius, axis length;
+ *   first_point  DEVICE (m+1) int64: exclusive prefix sum of the per-cylinder point counts (first_point[m] = cloud size).
+ * The call writes rows point0 .. point0+n of the cloud to out_points (DEVICE (n,3) float64; out_points_f32, optional, the
+ * same rows rounded to float32 as Modules/Utils.py:236 load_cloud would hand them to the labeller).  Variates:
+ *   theta/z/noise all NULL: drawn from Philox4x32-10, counter = (point number, block 0/1), key = seed — angle 2*pi*u,
+ *     axial position L*u, radial noise exp(-3 + 0.85*g) with g = sqrt(-2 ln(1-u1)) cos(2*pi*u2) (np.random.uniform /
+ *     np.random.lognormal(-3, 0.85) of :64-68 in distribution); a cloud depends on (table, seed) only, not on how the
+ *     rows are split over calls or ranks;
+ *   all three given (DEVICE (n,) float64, row i of this call): used as is — this is how the parity tests replay the
+ *     reference's own Mersenne-Twister draws.
+ * float64 arithmetic in the reference's order.  n == 0 is a no-op; m == 0 with n > 0 is TM_ERR_NO_CYLINDERS.
+ */
+int tm_noise_cloud(tm_handle *h, const double *cyl_rec, const int64_t *first_point, int64_t m, int64_t n, int64_t point0,
+                   uint64_t seed, const double *theta, const double *z, const double *noise,
+                   double *out_points, float *out_points_f32, void *stream);
 
 /*
  * How the last tm_label_cloud_host call moved its results: with >= 4 host threads available the (N,7) float64 records are

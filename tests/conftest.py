@@ -20,7 +20,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-OTHER_FIXTURES = {"proximity", "features", "drivers"}      # fixtures of other entry points, with their own tests
+OTHER_FIXTURES = {"proximity", "features", "drivers", "noise"}      # fixtures of other entry points, with their own tests
 
 
 def golden_names():
