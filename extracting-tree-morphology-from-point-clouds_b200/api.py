@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -41,6 +42,14 @@ MODES = {"auto": B.TM_MODE_AUTO, "brute": B.TM_MODE_BRUTE, "grid": B.TM_MODE_GRI
 def _require_cuda() -> None:
     if not torch.cuda.is_available():
         raise RuntimeError("treemorph_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+_pinned_live = 0            # bytes of page-locked result arrays currently alive (Engine._new_records)
+
+
+def _pinned_released(nbytes: int) -> None:
+    global _pinned_live
+    _pinned_live -= nbytes
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -210,15 +219,25 @@ class Engine:
 
     @staticmethod
     def _new_records(n: int) -> np.ndarray:
-        """The (N,7) float64 result array.  TM_PINNED_OUT=1 makes it page-locked (torch's caching host allocator, so
-        repeated calls reuse the block; arrays above TM_PINNED_OUT_MAX_MB, default 4096, stay pageable): no first-touch page
-        faults, ~10 % off a 10M-point call, at the price of memory that stays locked in torch's cache."""
+        """The (N,7) float64 result array.  Page-locked by default (torch's caching host allocator, so repeated calls reuse
+        the block): a fresh pageable array costs more in first-touch page faults than the labelling itself (10M points:
+        27 ms pageable, 16 ms page-locked, profiles/r01i_host_pipeline.md).  Bounded: arrays above TM_PINNED_OUT_MAX_MB
+        (default 4096) or beyond TM_PINNED_OUT_TOTAL_MB of live results (default 8192) are ordinary np.empty arrays, as is
+        everything with TM_PINNED_OUT=0."""
+        global _pinned_live
         nbytes = n * 56
-        if n > 0 and os.environ.get("TM_PINNED_OUT", "0") == "1" and nbytes <= int(os.environ.get("TM_PINNED_OUT_MAX_MB", "4096")) << 20:
+        if (n > 0 and os.environ.get("TM_PINNED_OUT", "1") != "0"
+                and nbytes <= int(os.environ.get("TM_PINNED_OUT_MAX_MB", "4096")) << 20
+                and _pinned_live + nbytes <= int(os.environ.get("TM_PINNED_OUT_TOTAL_MB", "8192")) << 20):
             try:
-                return torch.empty((n, 7), dtype=torch.float64, pin_memory=True).numpy()
+                t = torch.empty((n, 7), dtype=torch.float64, pin_memory=True)
             except RuntimeError:
-                pass
+                t = None
+            if t is not None:
+                out = t.numpy()
+                _pinned_live += nbytes
+                weakref.finalize(out.base, _pinned_released, nbytes)      # the tensor object numpy keeps as the array's base
+                return out
         return np.empty((n, 7), dtype=np.float64)
 
     # -- small-table fast path (QSMFittingDepthFirst.py:1006-1094) ---------------------------------

@@ -315,11 +315,11 @@ int tm_destroy(tm_handle *h) {
                           &h->pend_idx, &h->brute_slots, &h->pend_done, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
                           &h->small_out};
     for (auto *b : bufs) b->release();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < tmn::PIPE_SLOTS; ++i) {
         h->chunk_in[i].release(); h->chunk_rec[i].release(); h->chunk_off[i].release(); h->chunk_id[i].release();
         h->chunk_dist[i].release();
-        if (h->pinned_in[i]) cudaFreeHost(h->pinned_in[i]);
-        if (h->pinned_out[i]) cudaFreeHost(h->pinned_out[i]);
+        h->pinned_in[i].release();
+        h->pinned_out[i].release();
     }
     if (h->small_stream) cudaStreamDestroy(h->small_stream);
     delete h->pool;
@@ -543,7 +543,8 @@ static void assemble_rows_host(const T *cloud, int64_t row_stride, const float4 
 }
 
 // tm_label_cloud_host, host-assembly variant: per chunk H2D -> label (packed {offset, id}) -> D2H 16 B/point, while the
-// host workers assemble the previous chunk's records.
+// host workers assemble earlier chunks' records.  Up to PIPE_SLOTS chunks are in flight; a chunk's buffers are reused
+// only after the chunk has been assembled (hence fully transferred).
 static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride,
                                      const tm_params *params, double *out_records_host, float *out_dist_host, unsigned nthreads) {
     if (!h->pool || h->pool->n != nthreads) {
@@ -551,33 +552,27 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
         h->pool = new (std::nothrow) tmn::HostPool(nthreads);
         if (!h->pool) return tmn::fail(h, TM_ERR_NOMEM, "host worker pool%s%s");
     }
-    cudaStream_t s_in = h->pipe_stream[0], s_cmp = h->pipe_stream[1], s_out = h->pipe_stream[2];
-    h->host_d2h_bytes_per_point = 16 + (out_dist_host ? 4 : 0);
+    cudaStream_t s_in = h->pipe_stream[0], s_cmp = h->pipe_stream[1], s_out = h->pipe_stream[2], s_rows = h->pipe_stream[3];
     h->host_assembly_threads = static_cast<int32_t>(nthreads);
     int64_t chunk = 1 << 20;
     if (const char *env = getenv("TM_HOST_CHUNK")) { const long long v = atoll(env); if (v >= 1024) chunk = v; }
     chunk = std::min(chunk, n);
+    int depth = tmn::PIPE_SLOTS;
+    if (const char *env = getenv("TM_HOST_DEPTH")) depth = std::max(2, std::min(tmn::PIPE_SLOTS, atoi(env)));
     const size_t esz = dtype == TM_F32 ? 4 : 8;
     const bool in_pinned = host_is_pinned(cloud_host);
     const size_t in_bytes = static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
     const size_t pk_bytes = static_cast<size_t>(chunk) * sizeof(float4);
     const size_t out_bytes = pk_bytes + static_cast<size_t>(chunk) * sizeof(float);
-    // A pinned record array can also be written by the copy engine: TM_HOST_SPLIT=1..100 percent of the chunks are
-    // assembled on the device and DMA'd straight into the caller's rows (56 B/point over PCIe) while the host workers
-    // assemble the others (16 B/point).  Off by default: on the hosts measured (profiles/r01i_host_pipeline.md) the
-    // record array's DRAM write bandwidth is the limit either way, and the two writers only get in each other's way.
+    // A pinned record array can also be written by the copy engine: TM_HOST_SPLIT percent of the chunks are assembled on
+    // the device and DMA'd straight into the caller's rows (56 B/point over PCIe, on their own stream) while the host
+    // workers assemble the others (16 B/point + the host's stores).  See profiles/r01i_host_pipeline.md.
     int split = 0;
     if (const char *env = getenv("TM_HOST_SPLIT")) { if (host_is_pinned(out_records_host)) split = std::max(0, std::min(100, atoi(env))); }
     auto on_device = [split](int64_t c) { return ((c + 1) * split) / 100 > (c * split) / 100; };
-    for (int b = 0; b < 2; ++b) {
-        if (!in_pinned && h->pinned_in_cap < in_bytes) {
-            if (h->pinned_in[b]) { cudaFreeHost(h->pinned_in[b]); h->pinned_in[b] = nullptr; }
-            TM_CUDA(h, cudaMallocHost(&h->pinned_in[b], in_bytes));
-        }
-        if (h->pinned_out_cap < out_bytes) {
-            if (h->pinned_out[b]) { cudaFreeHost(h->pinned_out[b]); h->pinned_out[b] = nullptr; }
-            TM_CUDA(h, cudaMallocHost(&h->pinned_out[b], out_bytes));
-        }
+    for (int b = 0; b < depth; ++b) {
+        if (!in_pinned) TM_CUDA(h, h->pinned_in[b].ensure(in_bytes));
+        TM_CUDA(h, h->pinned_out[b].ensure(out_bytes));
         TM_CUDA(h, h->chunk_in[b].ensure(in_bytes + (dtype == TM_F64 ? static_cast<size_t>(chunk) * 12 : 0)));
         TM_CUDA(h, h->chunk_packed[b].ensure(pk_bytes));
         TM_CUDA(h, h->chunk_dist[b].ensure(static_cast<size_t>(chunk) * 4));
@@ -587,10 +582,9 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
             TM_CUDA(h, h->chunk_id[b].ensure(static_cast<size_t>(chunk) * 4));
         }
     }
-    if (!in_pinned) h->pinned_in_cap = std::max(h->pinned_in_cap, in_bytes);
-    h->pinned_out_cap = std::max(h->pinned_out_cap, out_bytes);
 
-    // events: [0,1] H2D done per buffer, [2,3] compute done, [4,5] D2H done
+    // events per slot b: [b] H2D done, [SLOTS + b] label done, [2 SLOTS + b] D2H done
+    constexpr int EV_H2D = 0, EV_CMP = tmn::PIPE_SLOTS, EV_D2H = 2 * tmn::PIPE_SLOTS;
     tm_stats total{};
     size_t d2h_total = 0;
     const bool trace = getenv("TM_TRACE_HOST") != nullptr;
@@ -600,49 +594,23 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     const int64_t nchunks = (n + chunk - 1) / chunk;
     const unsigned char *src = static_cast<const unsigned char *>(cloud_host);
-    auto assemble = [&](int64_t c) -> int {
-        const int b = static_cast<int>(c & 1);
-        const int64_t cnt = std::min(chunk, n - c * chunk);
-        const double w0 = now();
-        TM_CUDA(h, cudaEventSynchronize(h->pipe_event[4 + b]));
-        const double w1 = now();
-        t_wait += w1 - w0;
-        if (!on_device(c)) {
-            const float4 *packed = static_cast<const float4 *>(h->pinned_out[b]);
-            const unsigned char *crow = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
-            double *orow = out_records_host + c * chunk * 7;
-            h->pool->run([=](unsigned t, unsigned nt) {
-                const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
-                if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1);
-                else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1);
-            });
-        }
-        if (out_dist_host)
-            memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b]) + pk_bytes, static_cast<size_t>(cnt) * sizeof(float));
-        t_asm += now() - w1;
-        return TM_OK;
-    };
-    int rc = TM_OK;
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int b = static_cast<int>(c & 1);
+
+    auto issue = [&](int64_t c) -> int {
+        const int b = static_cast<int>(c % depth);
         const int64_t cnt = std::min(chunk, n - c * chunk);
         const size_t bytes = static_cast<size_t>(cnt) * static_cast<size_t>(row_stride) * esz;
         const unsigned char *csrc = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
-        // buffers b were last used by chunk c-2, which was assembled (hence fully transferred) in iteration c-1
         const double i0 = now();
         if (!in_pinned) {
-            par_memcpy(h->pinned_in[b], csrc, bytes);
+            par_memcpy(h->pinned_in[b].p, csrc, bytes);
             t_stage += now() - i0;
         }
         tmark(s_in);
-        if (!in_pinned) {
-            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b], bytes, cudaMemcpyHostToDevice, s_in));
-        } else {
-            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
-        }
+        TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, in_pinned ? static_cast<const void *>(csrc) : h->pinned_in[b].p, bytes,
+                                   cudaMemcpyHostToDevice, s_in));
         tmark(s_in);
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[0 + b], s_in));
-        TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[0 + b], 0));
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[EV_H2D + b], s_in));
+        TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[EV_H2D + b], 0));
         const float *pts32;
         int64_t stride32;
         if (dtype == TM_F64) {
@@ -661,7 +629,7 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
         LabelArgs a{pts32, cnt, stride32, *params, nullptr, dev ? h->chunk_id[b].as<int32_t>() : nullptr,
                     out_dist_host ? h->chunk_dist[b].as<float>() : nullptr, dev ? h->chunk_off[b].as<float>() : nullptr, nullptr, s_cmp};
         if (!dev) a.out_packed = h->chunk_packed[b].as<float4>();
-        rc = label_dispatch(h, a);
+        int rc = label_dispatch(h, a);
         if (rc != TM_OK) return rc;
         total.pairs_evaluated += h->stats.pairs_evaluated;
         total.points_brute += h->stats.points_brute;
@@ -672,49 +640,73 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
             if (rc != TM_OK) return rc;
         }
         tmark(s_cmp);
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[2 + b], s_cmp));
-        TM_CUDA(h, cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[EV_CMP + b], s_cmp));
+        cudaStream_t so = dev ? s_rows : s_out;
+        TM_CUDA(h, cudaStreamWaitEvent(so, h->pipe_event[EV_CMP + b], 0));
         if (dev) {
             TM_CUDA(h, cudaMemcpyAsync(out_records_host + c * chunk * 7, h->chunk_rec[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double),
-                                       cudaMemcpyDeviceToHost, s_out));
+                                       cudaMemcpyDeviceToHost, so));
             d2h_total += static_cast<size_t>(cnt) * 56;
         } else {
-            TM_CUDA(h, cudaMemcpyAsync(h->pinned_out[b], h->chunk_packed[b].p, static_cast<size_t>(cnt) * sizeof(float4),
-                                       cudaMemcpyDeviceToHost, s_out));
+            TM_CUDA(h, cudaMemcpyAsync(h->pinned_out[b].p, h->chunk_packed[b].p, static_cast<size_t>(cnt) * sizeof(float4),
+                                       cudaMemcpyDeviceToHost, so));
             d2h_total += static_cast<size_t>(cnt) * 16;
         }
         if (out_dist_host)
-            TM_CUDA(h, cudaMemcpyAsync(static_cast<unsigned char *>(h->pinned_out[b]) + pk_bytes, h->chunk_dist[b].p,
-                                       static_cast<size_t>(cnt) * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-        tmark(s_out);
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[4 + b], s_out));
+            TM_CUDA(h, cudaMemcpyAsync(static_cast<unsigned char *>(h->pinned_out[b].p) + pk_bytes, h->chunk_dist[b].p,
+                                       static_cast<size_t>(cnt) * sizeof(float), cudaMemcpyDeviceToHost, so));
+        tmark(so);
+        TM_CUDA(h, cudaEventRecord(h->pipe_event[EV_D2H + b], so));
         t_issue += now() - i0;
-        if (c >= 1) {
-            // the s_cmp work of chunk c must not overwrite chunk_packed / chunk_in of chunk c+1's buffer pair before the
-            // transfers of chunk c-1 are done: assembling c-1 here (it waits for its D2H) gives exactly that order
-            rc = assemble(c - 1);
-            if (rc != TM_OK) return rc;
+        return TM_OK;
+    };
+    auto assemble = [&](int64_t c) -> int {
+        const int b = static_cast<int>(c % depth);
+        const int64_t cnt = std::min(chunk, n - c * chunk);
+        const double w0 = now();
+        TM_CUDA(h, cudaEventSynchronize(h->pipe_event[EV_D2H + b]));
+        const double w1 = now();
+        t_wait += w1 - w0;
+        if (!on_device(c)) {
+            const float4 *packed = static_cast<const float4 *>(h->pinned_out[b].p);
+            const unsigned char *crow = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+            double *orow = out_records_host + c * chunk * 7;
+            h->pool->run([=](unsigned t, unsigned nt) {
+                const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
+                if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1);
+                else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1);
+            });
         }
+        if (out_dist_host)
+            memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b].p) + pk_bytes, static_cast<size_t>(cnt) * sizeof(float));
+        t_asm += now() - w1;
+        return TM_OK;
+    };
+
+    int64_t issued = 0;
+    for (int64_t done = 0; done < nchunks; ++done) {
+        while (issued < nchunks && issued - done < depth) {
+            const int rc = issue(issued++);
+            if (rc != TM_OK) { cudaDeviceSynchronize(); return rc; }
+        }
+        const int rc = assemble(done);
+        if (rc != TM_OK) { cudaDeviceSynchronize(); return rc; }
     }
-    rc = assemble(nchunks - 1);
-    if (rc != TM_OK) return rc;
     TM_CUDA(h, cudaStreamSynchronize(s_cmp));
     h->stats.pairs_evaluated = total.pairs_evaluated;
     h->stats.points_brute = total.points_brute;
     if (trace) {
-        float h2d = 0, lab = 0, d2h = 0, span = 0, ms = 0;
+        float h2d = 0, lab = 0, d2h = 0, ms = 0;
         for (size_t c = 0; c + 3 < tev.size(); c += 4) {
             cudaEventElapsedTime(&ms, tev[c], tev[c + 1]); h2d += ms;
             cudaEventElapsedTime(&ms, tev[c + 1], tev[c + 2]); lab += ms;
             cudaEventElapsedTime(&ms, tev[c + 2], tev[c + 3]); d2h += ms;
         }
-        if (tev.size() >= 4) cudaEventElapsedTime(&span, tev.front(), tev.back());
-        fprintf(stderr, "[tm host] device side: H2D %.3f ms, H2D end -> label end %.3f, label end -> D2H end %.3f, first H2D -> last D2H %.3f\n", h2d, lab, d2h, span);
+        fprintf(stderr, "[tm host] device side, summed over chunks: H2D %.3f ms, H2D end -> label end %.3f, label end -> D2H end %.3f\n", h2d, lab, d2h);
         for (auto e : tev) cudaEventDestroy(e);
+        fprintf(stderr, "[tm host] %lld chunks of %lld, %d in flight: issue %.3f ms (of which staging %.3f), wait for D2H %.3f, assemble %.3f\n",
+                static_cast<long long>(nchunks), static_cast<long long>(chunk), depth, t_issue, t_stage, t_wait, t_asm);
     }
-    if (trace)
-        fprintf(stderr, "[tm host] %lld chunks of %lld: issue %.3f ms (of which staging %.3f), wait for D2H %.3f, assemble %.3f\n",
-                static_cast<long long>(nchunks), static_cast<long long>(chunk), t_issue, t_stage, t_wait, t_asm);
     h->host_d2h_bytes_per_point = static_cast<int32_t>((d2h_total + static_cast<size_t>(n) / 2) / static_cast<size_t>(n)) + (out_dist_host ? 4 : 0);
     return TM_OK;
 }
@@ -761,22 +753,14 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
     const size_t rec_bytes = static_cast<size_t>(chunk) * 7 * sizeof(double);
     const size_t out_bytes = rec_bytes + static_cast<size_t>(chunk) * sizeof(float);
     for (int b = 0; b < 2; ++b) {
-        if (!in_pinned && h->pinned_in_cap < in_bytes) {
-            if (h->pinned_in[b]) { cudaFreeHost(h->pinned_in[b]); h->pinned_in[b] = nullptr; }
-            TM_CUDA(h, cudaMallocHost(&h->pinned_in[b], in_bytes));
-        }
-        if (!out_pinned && h->pinned_out_cap < out_bytes) {
-            if (h->pinned_out[b]) { cudaFreeHost(h->pinned_out[b]); h->pinned_out[b] = nullptr; }
-            TM_CUDA(h, cudaMallocHost(&h->pinned_out[b], out_bytes));
-        }
+        if (!in_pinned) TM_CUDA(h, h->pinned_in[b].ensure(in_bytes));
+        if (!out_pinned) TM_CUDA(h, h->pinned_out[b].ensure(out_bytes));
         TM_CUDA(h, h->chunk_in[b].ensure(in_bytes + (dtype == TM_F64 ? static_cast<size_t>(chunk) * 12 : 0)));
         TM_CUDA(h, h->chunk_rec[b].ensure(rec_bytes));
         TM_CUDA(h, h->chunk_off[b].ensure(static_cast<size_t>(chunk) * 12));
         TM_CUDA(h, h->chunk_id[b].ensure(static_cast<size_t>(chunk) * 4));
         TM_CUDA(h, h->chunk_dist[b].ensure(static_cast<size_t>(chunk) * 4));
     }
-    if (!in_pinned) h->pinned_in_cap = std::max(h->pinned_in_cap, in_bytes);
-    if (!out_pinned) h->pinned_out_cap = std::max(h->pinned_out_cap, out_bytes);
 
     // events: [0,1] H2D done per buffer, [2,3] compute done, [4,5] D2H done, [6,7] compute consumed input
     tm_stats total{};
@@ -787,9 +771,9 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         TM_CUDA(h, cudaEventSynchronize(h->pipe_event[4 + b]));
         if (!out_pinned) {
             const int64_t cnt = std::min(chunk, n - c * chunk);
-            par_memcpy(out_records_host + c * chunk * 7, h->pinned_out[b], static_cast<size_t>(cnt) * 7 * sizeof(double));
+            par_memcpy(out_records_host + c * chunk * 7, h->pinned_out[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double));
             if (out_dist_host)
-                memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b]) + rec_bytes,
+                memcpy(out_dist_host + c * chunk, static_cast<unsigned char *>(h->pinned_out[b].p) + rec_bytes,
                        static_cast<size_t>(cnt) * sizeof(float));
         }
         return TM_OK;
@@ -806,8 +790,8 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
             TM_CUDA(h, cudaStreamWaitEvent(s_in, h->pipe_event[6 + b], 0));
         }
         if (!in_pinned) {
-            par_memcpy(h->pinned_in[b], csrc, bytes);
-            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b], bytes, cudaMemcpyHostToDevice, s_in));
+            par_memcpy(h->pinned_in[b].p, csrc, bytes);
+            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b].p, bytes, cudaMemcpyHostToDevice, s_in));
         } else {
             TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
         }
@@ -842,12 +826,12 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         TM_CUDA(h, cudaEventRecord(h->pipe_event[2 + b], s_cmp));
         TM_CUDA(h, cudaEventRecord(h->pipe_event[6 + b], s_cmp));
         TM_CUDA(h, cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
-        double *dst_rec = out_pinned ? out_records_host + c * chunk * 7 : static_cast<double *>(h->pinned_out[b]);
+        double *dst_rec = out_pinned ? out_records_host + c * chunk * 7 : static_cast<double *>(h->pinned_out[b].p);
         TM_CUDA(h, cudaMemcpyAsync(dst_rec, h->chunk_rec[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double),
                                    cudaMemcpyDeviceToHost, s_out));
         if (out_dist_host) {
             float *dst_d = out_pinned ? out_dist_host + c * chunk
-                                      : reinterpret_cast<float *>(static_cast<unsigned char *>(h->pinned_out[b]) + rec_bytes);
+                                      : reinterpret_cast<float *>(static_cast<unsigned char *>(h->pinned_out[b].p) + rec_bytes);
             TM_CUDA(h, cudaMemcpyAsync(dst_d, h->chunk_dist[b].p, static_cast<size_t>(cnt) * sizeof(float),
                                        cudaMemcpyDeviceToHost, s_out));
         }
@@ -920,16 +904,8 @@ int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
     const size_t cyl_bytes = sizeof(float) * 7 * static_cast<size_t>(m);
     TM_CUDA(h, h->small_in.ensure(idx_bytes + cyl_bytes));
     TM_CUDA(h, h->small_out.ensure(static_cast<size_t>(n) * 9 + 16));
-    if (h->pinned_in_cap < idx_bytes + cyl_bytes || !h->pinned_in[0]) {
-        if (h->pinned_in[0]) { cudaFreeHost(h->pinned_in[0]); h->pinned_in[0] = nullptr; }
-        if (h->pinned_in[1]) { cudaFreeHost(h->pinned_in[1]); h->pinned_in[1] = nullptr; }
-        h->pinned_in_cap = 0;
-        const size_t want = std::max<size_t>(idx_bytes + cyl_bytes, 1 << 20);
-        TM_CUDA(h, cudaMallocHost(&h->pinned_in[0], want));
-        TM_CUDA(h, cudaMallocHost(&h->pinned_in[1], want));
-        h->pinned_in_cap = want;
-    }
-    unsigned char *stage = static_cast<unsigned char *>(h->pinned_in[0]);
+    TM_CUDA(h, h->pinned_in[0].ensure(std::max<size_t>(idx_bytes + cyl_bytes, 1 << 20)));
+    unsigned char *stage = static_cast<unsigned char *>(h->pinned_in[0].p);
     if (subset_host) memcpy(stage, subset_host, idx_bytes);
     float *cyl = reinterpret_cast<float *>(stage + idx_bytes);
     for (int64_t c = 0; c < m; ++c) {

@@ -34,6 +34,28 @@ struct DevBuf {
     T *as() const { return static_cast<T *>(p); }
 };
 
+// Page-locked host staging, grow-only.
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int PIPE_SLOTS = 4;          // chunks in flight in tm_label_cloud_host
+
 // Uniform voxel grid over the cylinders' solid AABBs (plus a margin).  Voxel (x,y,z) has the
 // linear id morton-interleaved over (bits.x, bits.y, bits.z) so that neighbouring voxels are
 // neighbours in memory and consecutive work items share candidate cylinders in L1/L2.
@@ -120,12 +142,11 @@ struct tm_handle {
     tmn::DevBuf scratch_f;           // misc float scratch
 
     // ---- host pipeline (tm_label_cloud_host) ----
-    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t pipe_event[8] = {nullptr};
-    void *pinned_in[2] = {nullptr, nullptr};
-    void *pinned_out[2] = {nullptr, nullptr};
-    size_t pinned_in_cap = 0, pinned_out_cap = 0;
-    tmn::DevBuf chunk_in[2], chunk_rec[2], chunk_off[2], chunk_id[2], chunk_dist[2];
+    cudaStream_t pipe_stream[4] = {nullptr, nullptr, nullptr, nullptr};      // H2D, label, D2H, D2H of device-assembled rows
+    cudaEvent_t pipe_event[4 * tmn::PIPE_SLOTS] = {nullptr};
+    tmn::PinnedBuf pinned_in[tmn::PIPE_SLOTS], pinned_out[tmn::PIPE_SLOTS];
+    tmn::DevBuf chunk_in[tmn::PIPE_SLOTS], chunk_rec[tmn::PIPE_SLOTS], chunk_off[tmn::PIPE_SLOTS], chunk_id[tmn::PIPE_SLOTS],
+        chunk_dist[tmn::PIPE_SLOTS];
 
     // ---- small-table fast path (tm_cloud_upload_host / tm_proximity_flags_host) ----
     tmn::DevBuf cloud_res;           // resident (n,3) fp32 copy of the caller's cloud
@@ -136,7 +157,7 @@ struct tm_handle {
 
     tmn::HostPool *pool = nullptr;   // host worker threads that assemble the (N,7) float64 records
     int32_t host_d2h_bytes_per_point = 0, host_assembly_threads = 0;     // what the last tm_label_cloud_host call did
-    tmn::DevBuf chunk_packed[2];
+    tmn::DevBuf chunk_packed[tmn::PIPE_SLOTS];
 
     // ---- point features (tm_knn.cu) ----
     tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box;

@@ -16,24 +16,26 @@ eng.set_cylinders(*[torch.tensor(x, device=dev) for x in (s, r, l, u)], torch.te
 cin = torch.empty((n, 3), dtype=torch.float32, pin_memory=True); cin.numpy()[:] = pts
 out = torch.empty((n, 7), dtype=torch.float64, pin_memory=True)
 ref = None
-for chunk in (1 << 20, 1 << 19, 1 << 18):
-    os.environ["TM_HOST_CHUNK"] = str(chunk)
-    for split in (0, 25, 40, 50, 60, 75, 100):
-        os.environ["TM_HOST_SPLIT"] = str(split)
-        ts = []
-        for rep in range(6):
-            t0 = time.perf_counter()
-            eng.label_cloud_host(cin.numpy(), api.VARIANT_A, out=out.numpy())
-            ts.append(time.perf_counter() - t0)
-        if ref is None:
-            ref = out.numpy().copy()
-        same = bool(np.array_equal(ref, out.numpy(), equal_nan=True))
-        t = float(np.median(ts[2:]))
-        print(json.dumps({"chunk": chunk, "split_pct": split, "ms": round(1e3 * t, 3), "gpts_per_s": round(n / t / 1e9, 3),
-                          "d2h_bytes_per_point": eng.host_pipeline_info()["d2h_bytes_per_point"], "same_rows": same}), flush=True)
+for depth in (2, 3, 4):
+    os.environ["TM_HOST_DEPTH"] = str(depth)
+    for chunk in (1 << 20, 1 << 19):
+        os.environ["TM_HOST_CHUNK"] = str(chunk)
+        for split in (0, 15, 20, 25, 30, 40, 100):
+            os.environ["TM_HOST_SPLIT"] = str(split)
+            ts = []
+            for rep in range(7):
+                t0 = time.perf_counter()
+                eng.label_cloud_host(cin.numpy(), api.VARIANT_A, out=out.numpy())
+                ts.append(time.perf_counter() - t0)
+            if ref is None:
+                ref = out.numpy().copy()
+            same = bool(np.array_equal(ref, out.numpy(), equal_nan=True))
+            t = float(np.median(ts[2:]))
+            print(json.dumps({"in_flight": depth, "chunk": chunk, "split_pct": split, "ms": round(1e3 * t, 3), "gpts_per_s": round(n / t / 1e9, 3),
+                              "d2h_bytes_per_point": eng.host_pipeline_info()["d2h_bytes_per_point"], "same_rows": same}), flush=True)
 # the drop-in call as a user makes it: pageable float64 cloud in, the engine allocates the records
 cloud64 = pts.astype(np.float64)
-for k in ("TM_HOST_CHUNK", "TM_HOST_SPLIT"):
+for k in ("TM_HOST_CHUNK", "TM_HOST_SPLIT", "TM_HOST_DEPTH"):
     os.environ.pop(k, None)
 for pinned in ("0", "1"):
     os.environ["TM_PINNED_OUT"] = pinned

@@ -7,6 +7,8 @@
 Tolerances (BASELINE.json north_star): cylinder indices exact except near-ties (top-2 distances within
 1e-6 relative); offsets and distances within 1e-5 m.  In practice the kernels are bit-identical.
 """
+import gc
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -369,9 +371,20 @@ def test_host_pipeline_variants_agree(eng, f64, monkeypatch):
         rec, dist = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid", want_dist=True, out=out)
         assert rec is out and abs(eng.host_pipeline_info()["d2h_bytes_per_point"] - per_point) <= 6
         assert np.array_equal(rec, outs["0"][0], equal_nan=True) and np.array_equal(dist, ora["dist"], equal_nan=True)
-    monkeypatch.setenv("TM_PINNED_OUT", "1")                                 # the engine allocates a page-locked array
+    for pinned in ("1", "0"):                                                # result array allocated by the engine
+        monkeypatch.setenv("TM_PINNED_OUT", pinned)
+        rec = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid")
+        assert torch.from_numpy(rec).is_pinned() == (pinned == "1")
+        assert np.array_equal(rec, outs["0"][0], equal_nan=True)
+    monkeypatch.setenv("TM_PINNED_OUT", "1")
+    live = api._pinned_live
     rec = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid")
-    assert np.array_equal(rec, outs["0"][0], equal_nan=True)
+    assert api._pinned_live == live + rec.nbytes
+    del rec
+    gc.collect()
+    assert api._pinned_live == live                                          # freed arrays give their budget back
+    monkeypatch.setenv("TM_PINNED_OUT_TOTAL_MB", "0")
+    assert not torch.from_numpy(eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid")).is_pinned()
 
 
 def _fuzz_case(rng):
