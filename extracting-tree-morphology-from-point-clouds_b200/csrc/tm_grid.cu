@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) 
 // ------------------------------------------------------------------------------------------------
 constexpr int RING_MAX = 8;
 constexpr unsigned int RING_LIMIT = 32768;     // pending points beyond which the tree search is faster (measured crossover ~50k)
-constexpr int RING_WARPS = 8;
+constexpr int RING_WARPS = 4;
 
 struct RingArgs {
     const float *pts;
@@ -1026,7 +1026,9 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 //   sweep:   the entries of all listed tiles form one flat index space, thread t takes entries t, t + 256, ... (binary
 //            search of the list), runs the capsule cull against its incumbent and evaluates the survivors.
 // The threads' winners meet in a warp-shuffle min and a shared 64-bit atomicMin.
-constexpr int RING_LIST = 1024;         // candidate voxels per gather step
+constexpr int RING_LIST = RING_WARPS * 32 * 4;   // candidate voxels per gather step (4 per thread)
+constexpr int RING_LIST_LOG2 = 9;
+static_assert((1 << RING_LIST_LOG2) == RING_LIST, "RING_LIST must be a power of two");
 
 template <bool GUARD, bool NFMA>
 __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridDev g) {
@@ -1110,7 +1112,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
                 for (uint32_t e = tid; e < n_ent; e += RING_WARPS * 32) {
                     int lo = 0, hi = RING_LIST;            // last slot with s_beg[slot] <= e
 #pragma unroll
-                    for (int it = 0; it < 10; ++it) {
+                    for (int it = 0; it < RING_LIST_LOG2; ++it) {
                         const int mid = (lo + hi) >> 1;
                         if (s_beg[mid] <= e) lo = mid; else hi = mid;
                     }
@@ -1255,7 +1257,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     rg.tileA = h->tileA.as<float4>(); rg.tileB = h->tileB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
     rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
     rg.st = dst;
-    const int rg_blocks = h->sm_count * 8;
+    const int rg_blocks = h->sm_count * (2048 / (RING_WARPS * 32));
     if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
