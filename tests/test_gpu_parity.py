@@ -485,3 +485,39 @@ def test_full_size_properties(eng, n, m):
                           torch.tensor(length[j:j + 1], device=dev), torch.tensor(unit[j:j + 1], device=dev))
         one = eng.label(dpts[rows], api.VARIANT_A, mode="brute", want=("dist",))
         assert bool((one["dist"] == full["dist"][rows]).all())
+
+
+@pytest.mark.parametrize("vn", ["A", "B"])
+def test_largest_table_of_the_sweep(eng, vn):
+    """BASELINE.json configs[4]'s largest table (200k cylinders = a 40-tree plot) with 1M points, a tenth of them clutter
+    metres away from any cylinder (tree search): equal to the exhaustive kernel on a subset and to the oracle on a smaller one."""
+    from treemorph_b200 import synth
+    m, n = 200_000, 1_000_000
+    q = synth.random_qsm(m, seed=1003)
+    pts = synth.sample_points(q, n, seed=2003)
+    rng = np.random.default_rng(7)
+    lo, hi = pts.min(0), pts.max(0)
+    clutter = rng.choice(n, n // 10, replace=False)
+    pts[clutter] = (lo + rng.random((len(clutter), 3)) * (hi - lo)).astype(np.float32)
+    var = _oracle.VARIANTS[vn]
+    start, radius, length, unit, ids = synth.cylinder_arrays(q, var.axis_eps)
+    case = {"start": start, "radius": radius, "length": length, "unit": unit, "ids": ids, "variant": var, "points": pts}
+    _install(eng, case)
+    dev = eng.device
+    dpts = torch.tensor(pts, device=dev)
+    avar = api.VARIANTS[vn]
+    full = eng.label(dpts, avar, mode="grid", want=("index", "id", "dist", "offset"))
+    st = eng.stats()
+    assert st["mode_used"] == 2 and st["points_tree"] > 50_000
+    assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == n
+    sub_np = np.concatenate([rng.choice(n, 6_000, replace=False), clutter[:2_000]])
+    sub = torch.tensor(sub_np, device=dev)
+    brute = eng.label(dpts[sub], avar, mode="brute", want=("index", "id", "dist", "offset"))
+    for k in ("index", "id", "dist", "offset"):
+        a, b = full[k][sub], brute[k]
+        same = (a == b) | (torch.isnan(a) & torch.isnan(b)) if a.dtype.is_floating_point else (a == b)
+        assert bool(same.all()), f"{k}: grid != exhaustive on the subset"
+    osub = np.concatenate([sub_np[:600], sub_np[-200:]])
+    ora = oracle_label(case, pts[osub])
+    got = {k: full[k][torch.tensor(osub, device=dev)].cpu().numpy() for k in ("index", "id", "dist", "offset")}
+    assert_parity(got, ora, f"{n}x{m}/{vn} vs oracle", require_bitwise=True)
