@@ -79,7 +79,7 @@ struct DevStats {
     unsigned int n_brute;            // of those, points that need the exhaustive kernel (slots of brute_slots)
     unsigned int far_certified;      // points certified by the far part of their own tile (inside the tile kernel)
     unsigned int ring_certified;     // points certified by the ring search
-    unsigned int pad[1];
+    unsigned int bvh_cursor;         // next pending slot the tree search hands out
 };
 
 struct HostPool;                     // tm_api.cu
