@@ -211,7 +211,7 @@ constexpr int BVH_NODE_STEPS = 6;
 constexpr int32_t BVH_IDLE = 0x7fffffff;
 
 template <bool GUARD, bool NFMA>
-__global__ void __launch_bounds__(128) bvh_kernel(BvhArgs a) {
+__global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
     const unsigned int n_pend = *a.d_pending;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -366,7 +366,7 @@ int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst) {
     b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = h->maxabs; b.slack_floor = h->slack_floor;
     b.st = dst;
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
-    const int grid = h->sm_count * 16;
+    const int grid = h->sm_count * 12;
     if (guard) { if (nfma) bvh_kernel<true, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<true, false><<<grid, 128, 0, a.stream>>>(b); }
     else       { if (nfma) bvh_kernel<false, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<false, false><<<grid, 128, 0, a.stream>>>(b); }
     TM_KCHECK(h, a.stream, "bvh_kernel");
