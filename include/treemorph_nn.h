@@ -11,6 +11,12 @@
  *   generate_offset_cloud_cuda_batched  PreProcessing/LabelGenerationCuda.py:113-135
  *                                       Modules/Projection.py:117-144
  *
+ * and, either side of that path:
+ *
+ *   cylinder_proximity_based_segmentation  Modules/Pipeline/QSMFittingDepthFirst.py:1006-1094  (tm_proximity_flags_host)
+ *   compute_*_ckdtree / add_features       Modules/Features.py:111-229                         (tm_knn_covariance, tm_radius_count)
+ *   noiseGeneration                        PreProcessing/NoiseDataGeneration.py:14-106         (tm_noise_cloud)
+ *
  * Conventions
  *   - plain C: pointers, sizes, POD structs; no torch / C++ types cross this boundary;
  *   - every pointer is a DEVICE pointer on the handle's device unless the name ends in `_host`;
