@@ -379,6 +379,15 @@ def main():
                      "frac": pairs * OPS_PER_PAIR / (dom_ms * 1e-3) / fp32_peak if fp32_peak else None,
                      "peak_source": "FFMA/FADD+FMUL chain probe in this run"}
 
+    # whole step against HBM (compulsory bytes per point over the step), and the brute-force-equivalent pair
+    # rate N*M/t -- a speed-up figure of the pruning, not a roofline fraction
+    step_gbs = BYTES_PER_POINT * N_POINTS / (ms_per_step * 1e-3) / 1e9
+    step_view = {"compulsory_bytes_per_point": BYTES_PER_POINT, "achieved_GBps": step_gbs, "hbm_frac": step_gbs / hbm_peak,
+                 "dram_bytes_all_kernels": sum(NCU_DRAM_BYTES.values()) if (N_POINTS, N_CYLINDERS) == (10_000_000, 50_000) and args.mode == "grid" else None,
+                 "brute_force_equivalent_pairs_per_s": float(N_POINTS) * N_CYLINDERS / (ms_per_step * 1e-3),
+                 "brute_force_equivalent_lane_ops_per_s": float(N_POINTS) * N_CYLINDERS * OPS_PER_PAIR / (ms_per_step * 1e-3),
+                 "pairs_evaluated_per_point": pairs / N_POINTS, "cull_tests_per_point": stats["cull_tests"] / N_POINTS}
+
     # ---- exhaustive kernel as the FP32 yard-stick (pairs = N*M exactly)
     brute = None
     if not args.skip_brute:
@@ -422,7 +431,7 @@ def main():
                 "note": "with host_assembly_threads > 0 only {offset, id} (16 B/point) cross PCIe; the host workers write the 56 B records",
                 "steps": e2e_steps, "checked": e2e_ok},
         "gpu_launches": launches_per_step * steps,
-        "roofline": roofline, "fp32_roofline": fp32_roofline, "brute_force_yardstick": brute,
+        "roofline": roofline, "fp32_roofline": fp32_roofline, "step_view": step_view, "brute_force_yardstick": brute,
         "cpu_baseline": cpu,
         "phases_ms": phases, "stats": stats, "setup_ms": setup_ms, "table_broadcast_ms": bcast_ms,
         "input_generation_s": gen_s,
