@@ -104,6 +104,21 @@ def noise_cloud(cylinders: pd.DataFrame | CylinderPlan, device=None, seed: int |
     return out.cpu().numpy()
 
 
+def noise_cloud_sharded(cylinders: pd.DataFrame | CylinderPlan | None, device=None, seed: int = 0, src: int = 0):
+    """One process per GPU (torchrun): rank ``src`` holds the QSM, every rank generates its own contiguous rows of the cloud
+    (``sharding.noise_cloud_sharded``).  Returns (device tensor (k,3) float64, (lo, hi))."""
+    from .. import sharding
+    eng = api.get_engine(device)
+    plan = None
+    if cylinders is not None:
+        plan = cylinders if isinstance(cylinders, CylinderPlan) else cylinder_plan(cylinders)
+
+    def rows(rec, first, lo, hi, sd):
+        return eng.noise_cloud(rec.contiguous(), first.contiguous(), n=hi - lo, point0=lo, seed=sd)
+
+    return sharding.noise_cloud_sharded(rows, plan.records if plan else None, plan.first_point if plan else None, seed, eng.device, src)
+
+
 def noiseGeneration(data_root, npy_root):
     """
     inputs:

@@ -98,6 +98,40 @@ def label_sharded(label_fn, cloud: np.ndarray | None, table: torch.Tensor | None
     return label_fn(mine[: hi - lo].cpu().numpy(), table), (lo, hi)
 
 
+def noise_cloud_sharded(rows_fn, records: np.ndarray | None, first_point: np.ndarray | None, seed: int, device, src: int = 0):
+    """Noisy surface cloud of a QSM (PreProcessing/NoiseDataGeneration.py) across all ranks: `src` holds the per-cylinder
+    plan (``records`` (M,14) float64, ``first_point`` (M+1,) int64, see ``tm_noise_cloud``) and broadcasts it once together
+    with the seed; every rank then generates its own contiguous rows of the cloud.  The variates are a function of the
+    point number, so the union of the slices is the cloud a single process would have produced.
+
+    rows_fn(records tensor, first_point tensor, lo, hi, seed) -> the rows [lo, hi) of the cloud.
+    Returns (rows of this rank, (lo, hi)); there is no collective on the data path.
+    """
+    rank, size = world()
+    if size == 1:
+        rec = torch.as_tensor(records, dtype=torch.float64, device=device)
+        first = torch.as_tensor(first_point, dtype=torch.int64, device=device)
+        n = int(first[-1]) if len(first) else 0
+        return rows_fn(rec, first, 0, n, seed), (0, n)
+    meta = torch.zeros(2, dtype=torch.int64, device=device)
+    if rank == src:
+        meta[0], meta[1] = records.shape[0], np.int64(np.uint64(seed & (2 ** 64 - 1)).astype(np.int64))
+    dist.broadcast(meta, src=src)
+    m = int(meta[0])
+    seed = int(meta[1]) & (2 ** 64 - 1)
+    if rank == src:
+        rec = torch.as_tensor(np.ascontiguousarray(records, dtype=np.float64), device=device)
+        first = torch.as_tensor(np.ascontiguousarray(first_point, dtype=np.int64), device=device)
+    else:
+        rec = torch.empty((m, 14), dtype=torch.float64, device=device)
+        first = torch.empty(m + 1, dtype=torch.int64, device=device)
+    dist.broadcast(rec, src=src)
+    dist.broadcast(first, src=src)
+    n = int(first[-1])
+    lo, hi = shard_bounds(n, size, rank)
+    return rows_fn(rec, first, lo, hi, seed), (lo, hi)
+
+
 def gather_records(records: np.ndarray, device, dst: int = 0) -> np.ndarray | None:
     """Optional: concatenate every rank's (k,7) records on `dst` in rank order."""
     rank, size = world()

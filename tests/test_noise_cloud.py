@@ -123,6 +123,8 @@ def test_counter_based_cloud_equals_the_oracle_and_does_not_depend_on_sharding()
         part = eng.noise_cloud(rec, first, n=b - a, point0=a, seed=seed).cpu().numpy()
         assert np.array_equal(part, got[a:b])
         assert not np.array_equal(N.noise_cloud(df, "cuda:0", seed=seed + 1), got)
+        rows, (lo, hi) = N.noise_cloud_sharded(df, "cuda:0", seed=seed)          # one rank: the whole cloud
+        assert (lo, hi) == (0, hp.n_points) and np.array_equal(rows.cpu().numpy(), got)
 
 
 @pytest.mark.gpu

@@ -71,3 +71,44 @@ def test_two_rank_sharded_labelling_matches_single_process(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok.npy")
+
+
+def _noise_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import noise_cloud as nc
+        from treemorph_b200 import synth
+        from treemorph_b200.PreProcessing import NoiseDataGeneration as N
+        seed = 0xFEDC_BA98_7654_3210                          # needs all 64 bits to survive the broadcast
+        df = synth.qsm_dataframe(synth.random_qsm(80, seed=6))
+        plan = N.cylinder_plan(df)
+        records = first = None
+        if rank == 0:                                          # only the source rank holds the plan
+            records, first = plan.records, plan.first_point
+
+        def rows_fn(rec, first_point, lo, hi, sd):            # CPU stand-in for Engine.noise_cloud(point0=lo, n=hi-lo)
+            rec = rec.numpy()
+            p = nc.Plan(rec[:, 0:3], rec[:, 13], rec[:, 12], rec[:, 3:12].reshape(-1, 3, 3), np.diff(first_point.numpy()))
+            theta, z, noise = nc.philox_variates(p, sd, first=lo, n=hi - lo)
+            cid = nc.owners(p)[lo:hi]
+            rho = p.radius[cid] + noise
+            local = np.stack([rho * np.cos(theta), rho * np.sin(theta), z], axis=1)
+            return np.einsum("nij,nj->ni", p.rot[cid], local) + p.start[cid]
+
+        rows, (lo, hi) = sharding.noise_cloud_sharded(rows_fn, records, first, seed, torch.device("cpu"))
+        assert (lo, hi) == sharding.shard_bounds(plan.n_points, world, rank) and rows.shape == (hi - lo, 3)
+        op = nc.plan(df[["startX", "startY", "startZ"]].values, df[["endX", "endY", "endZ"]].values, df["radius"].values)
+        want = nc.place(op, *nc.philox_variates(op, seed))
+        assert np.array_equal(rows, want[lo:hi])               # the slices tile the single-process cloud exactly
+        np.save(os.path.join(tmpdir, f"ok{rank}.npy"), np.array([hi - lo]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_noise_cloud_tiles_the_single_process_cloud(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_noise_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0.npy") and os.path.exists(tmp_path / "ok1.npy")
