@@ -313,7 +313,7 @@ int tm_destroy(tm_handle *h) {
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->cell_count,
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
                           &h->pend_idx, &h->brute_slots, &h->pend_done, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
-                          &h->small_out};
+                          &h->small_out, &h->bvh_scratch};
     for (auto *b : bufs) b->release();
     for (int i = 0; i < tmn::PIPE_SLOTS; ++i) {
         h->chunk_in[i].release(); h->chunk_rec[i].release(); h->chunk_off[i].release(); h->chunk_id[i].release();
@@ -323,7 +323,6 @@ int tm_destroy(tm_handle *h) {
     }
     if (h->small_stream) cudaStreamDestroy(h->small_stream);
     delete h->pool;
-    if (h->bvh_pinned) cudaFreeHost(h->bvh_pinned);
     for (auto &b : h->chunk_packed) b.release();
     for (auto &s : h->pipe_stream) if (s) cudaStreamDestroy(s);
     for (auto &e : h->pipe_event) if (e) cudaEventDestroy(e);

@@ -5,8 +5,9 @@
 // every cylinder within d of its voxel — thousands in a crown — whereas a per-point tree descent with the incumbent as
 // the pruning radius visits O(log M) boxes plus the few leaves that are nearly as close as the winner.
 //
-//   build (per table, host):  Morton-order the regular cylinders by box centre, median-split the order recursively,
-//                             leaves of <= 4 cylinders, node = the two child boxes + child codes in one 64-byte record.
+//   build (per table, device): Morton-order the regular cylinders by box centre (radix sort), split the order in the
+//                             middle recursively, leaves of <= 4 cylinders, node = the two child boxes + child codes
+//                             in one 64-byte record; boxes bottom-up, one kernel.
 //   search (per call):        one THREAD per pending point, explicit stack in local memory, nearer child first, node
 //                             pruned when dist(p, box) > thr(incumbent); leaf cylinders go through the same capsule cull
 //                             and the reference-order evaluation as everywhere else.  The incumbent left by the tile
@@ -19,8 +20,8 @@
 // saw; for points outside the grid they are evaluated here.
 #include <algorithm>
 #include <cmath>
-#include <cstring>
-#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "tm_core.cuh"
 #include "tm_eval.cuh"
@@ -38,8 +39,13 @@ struct __align__(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "one node = two 32-byte sectors");
 
-// ---- host build ------------------------------------------------------------------------------------------------
-static inline uint32_t expand10(uint32_t v) {
+// ---- device build ---------------------------------------------------------------------------------------------
+// The tree over n Morton-ordered cylinders is the implicit "split the range in the middle" tree: its shape depends on n
+// alone, so nodes are numbered like a binary heap (root 1, children 2i and 2i+1) and every thread finds the range of its
+// slot by following the bits of the slot number from the root.  Boxes come bottom-up: one thread per leaf computes the
+// leaf's box and climbs; at every parent the second arrival (atomic counter) has both children's boxes in front of it,
+// writes the 64-byte node record and goes on.
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
     v &= 0x3ffu;
     v = (v | (v << 16)) & 0x030000FFu;
     v = (v | (v << 8)) & 0x0300F00Fu;
@@ -48,41 +54,83 @@ static inline uint32_t expand10(uint32_t v) {
     return v;
 }
 
-struct BuildCtx {
-    const float4 *lo, *hi;
-    const int32_t *order;
-    BvhNode *nodes;          // pinned staging
-    int n_nodes;
+struct __align__(16) BvhSlot {       // build scratch per heap slot: the subtree's box and range
+    float lo[3], hi[3];
+    int32_t first, count;
 };
 
-static void box_of(const BuildCtx &cx, int first, int count, float *lo, float *hi) {
-    for (int k = 0; k < 3; ++k) { lo[k] = INFINITY; hi[k] = -INFINITY; }
-    for (int i = first; i < first + count; ++i) {
-        const float4 a = cx.lo[cx.order[i]], b = cx.hi[cx.order[i]];
-        lo[0] = std::min(lo[0], a.x); lo[1] = std::min(lo[1], a.y); lo[2] = std::min(lo[2], a.z);
-        hi[0] = std::max(hi[0], b.x); hi[1] = std::max(hi[1], b.y); hi[2] = std::max(hi[2], b.z);
-    }
+// 64-bit sort key: Morton code of the box centre | row; special cylinders (not in the tree) sort to the end
+__global__ void bvh_key_kernel(const float4 *__restrict__ boxlo, const float4 *__restrict__ boxhi, int m, float ox, float oy, float oz,
+                               float sx, float sy, float sz, unsigned long long *__restrict__ keys) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const float4 a = boxlo[c], b = boxhi[c];
+    if (!(a.w == 0.f)) { keys[c] = 0xFFFFFFFF00000000ull | static_cast<uint32_t>(c); return; }
+    const uint32_t qx = static_cast<uint32_t>(fminf(fmaxf((0.5f * (a.x + b.x) - ox) * sx, 0.f), 1023.f));
+    const uint32_t qy = static_cast<uint32_t>(fminf(fmaxf((0.5f * (a.y + b.y) - oy) * sy, 0.f), 1023.f));
+    const uint32_t qz = static_cast<uint32_t>(fminf(fmaxf((0.5f * (a.z + b.z) - oz) * sz, 0.f), 1023.f));
+    const uint32_t code = expand10(qx) | (expand10(qy) << 1) | (expand10(qz) << 2);
+    keys[c] = (static_cast<unsigned long long>(code) << 32) | static_cast<uint32_t>(c);
 }
 
-// returns the child code of the subtree over order[first, first + count) and its box
-static int32_t build_range(BuildCtx &cx, int first, int count, float *lo, float *hi) {
-    if (count <= BVH_LEAF) {
-        box_of(cx, first, count, lo, hi);
-        return -1 - ((first << 3) | (count - 1));
+__device__ __forceinline__ int32_t bvh_child_ref(int slot, const BvhSlot &s) {
+    return s.count <= BVH_LEAF ? -1 - ((s.first << 3) | (s.count - 1)) : slot;
+}
+
+__global__ void bvh_build_kernel(const unsigned long long *__restrict__ sorted_keys, const float4 *__restrict__ boxlo,
+                                 const float4 *__restrict__ boxhi, int n, int slots, int32_t *__restrict__ rows,
+                                 BvhSlot *__restrict__ scratch, int *__restrict__ arrivals, BvhNode *__restrict__ nodes) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) rows[t] = static_cast<int32_t>(static_cast<uint32_t>(sorted_keys[t]));
+    int id = t + 1;                                             // heap slot 1 .. slots-1
+    if (id >= slots) return;
+    // range of this slot: follow the bits of the slot number below its leading one
+    int first = 0, count = n;
+    const int depth = 31 - __clz(id);
+    for (int b = depth - 1; b >= 0; --b) {
+        if (count <= BVH_LEAF) return;                          // an ancestor is a leaf: the slot does not exist
+        const int half = count / 2;
+        if ((id >> b) & 1) { first += half; count -= half; } else { count = half; }
     }
-    const int id = cx.n_nodes++;
-    const int half = count / 2;
-    float l0[3], h0[3], l1[3], h1[3];
-    const int32_t c0 = build_range(cx, first, half, l0, h0);
-    const int32_t c1 = build_range(cx, first + half, count - half, l1, h1);
-    BvhNode &n = cx.nodes[id];
-    for (int k = 0; k < 3; ++k) {
-        n.lo0[k] = l0[k]; n.hi0[k] = h0[k]; n.lo1[k] = l1[k]; n.hi1[k] = h1[k];
-        lo[k] = std::min(l0[k], l1[k]);
-        hi[k] = std::max(h0[k], h1[k]);
+    if (count > BVH_LEAF) return;                               // inner node: written by whichever child arrives second
+    BvhSlot me;
+    me.first = first; me.count = count;
+    for (int k = 0; k < 3; ++k) { me.lo[k] = INFINITY; me.hi[k] = -INFINITY; }
+    for (int i = first; i < first + count; ++i) {
+        const uint32_t r = static_cast<uint32_t>(sorted_keys[i]);
+        const float4 a = boxlo[r], b = boxhi[r];
+        me.lo[0] = fminf(me.lo[0], a.x); me.lo[1] = fminf(me.lo[1], a.y); me.lo[2] = fminf(me.lo[2], a.z);
+        me.hi[0] = fmaxf(me.hi[0], b.x); me.hi[1] = fmaxf(me.hi[1], b.y); me.hi[2] = fmaxf(me.hi[2], b.z);
     }
-    n.c0 = c0; n.c1 = c1; n.pad[0] = n.pad[1] = 0;
-    return id;
+    for (;;) {
+        scratch[id] = me;
+        if (id == 1) return;                                    // the root's own box is not needed
+        __threadfence();
+        const int parent = id >> 1;
+        if (atomicAdd(&arrivals[parent], 1) == 0) return;       // the sibling will finish the parent
+        __threadfence();
+        const volatile BvhSlot *vs = scratch;
+        BvhSlot c0, c1;
+        for (int k = 0; k < 3; ++k) {
+            c0.lo[k] = vs[2 * parent].lo[k]; c0.hi[k] = vs[2 * parent].hi[k];
+            c1.lo[k] = vs[2 * parent + 1].lo[k]; c1.hi[k] = vs[2 * parent + 1].hi[k];
+        }
+        c0.first = vs[2 * parent].first; c0.count = vs[2 * parent].count;
+        c1.first = vs[2 * parent + 1].first; c1.count = vs[2 * parent + 1].count;
+        BvhNode nd;
+        for (int k = 0; k < 3; ++k) {
+            nd.lo0[k] = c0.lo[k]; nd.hi0[k] = c0.hi[k]; nd.lo1[k] = c1.lo[k]; nd.hi1[k] = c1.hi[k];
+            me.lo[k] = fminf(c0.lo[k], c1.lo[k]);
+            me.hi[k] = fmaxf(c0.hi[k], c1.hi[k]);
+        }
+        nd.c0 = bvh_child_ref(2 * parent, c0);
+        nd.c1 = bvh_child_ref(2 * parent + 1, c1);
+        nd.pad[0] = nd.pad[1] = 0;
+        nodes[parent] = nd;
+        me.first = c0.first;
+        me.count = c0.count + c1.count;
+        id = parent;
+    }
 }
 
 __global__ void bvh_leaf_gather_kernel(const int32_t *__restrict__ rows, int n, const float4 *__restrict__ recAB,
@@ -94,82 +142,52 @@ __global__ void bvh_leaf_gather_kernel(const int32_t *__restrict__ rows, int n, 
     leafAB[2 * i + 1] = recAB[2 * r + 1];
 }
 
-int build_bvh(tm_handle *h, cudaStream_t stream) {
+// n_regular cylinders (boxlo.w == 0) inside [lo, hi] (both known to the caller from the packing pass)
+int build_bvh(tm_handle *h, cudaStream_t stream, int n_regular, const float *lo, const float *hi) {
     const int m = static_cast<int>(h->m);
+    const int n = n_regular;
     h->bvh_count = 0;
     h->bvh_root = 0;
     if (m > (1 << 27)) return fail(h, TM_ERR_INVALID, "tm_set_cylinders: more than 2^27 cylinders%s%s");
-    // pinned staging (grow-only, owned by the handle): pageable copies of a few MB cost more than the build itself
-    const size_t box_bytes = sizeof(float4) * 2 * static_cast<size_t>(m);
-    const size_t out_bytes = sizeof(BvhNode) * (static_cast<size_t>(m) / 2 + 2) + sizeof(int32_t) * static_cast<size_t>(m);
-    if (h->bvh_pinned_cap < box_bytes + out_bytes) {
-        if (h->bvh_pinned) cudaFreeHost(h->bvh_pinned);
-        h->bvh_pinned = nullptr;
-        h->bvh_pinned_cap = 0;
-        TM_CUDA(h, cudaMallocHost(&h->bvh_pinned, box_bytes + out_bytes + (1 << 16)));
-        h->bvh_pinned_cap = box_bytes + out_bytes + (1 << 16);
-    }
-    float4 *lo_p = static_cast<float4 *>(h->bvh_pinned), *hi_p = lo_p + m;
-    TM_CUDA(h, cudaMemcpyAsync(lo_p, h->boxlo.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
-    TM_CUDA(h, cudaMemcpyAsync(hi_p, h->boxhi.p, sizeof(float4) * m, cudaMemcpyDeviceToHost, stream));
-    TM_CUDA(h, cudaStreamSynchronize(stream));
-    struct Span { const float4 *p; const float4 &operator[](size_t i) const { return p[i]; } };
-    const Span lo{lo_p}, hi{hi_p};
-    BvhNode *nodes_p = reinterpret_cast<BvhNode *>(hi_p + m);
-    int32_t *order = reinterpret_cast<int32_t *>(nodes_p + (static_cast<size_t>(m) / 2 + 2));
-    int n = 0;
-    float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int c = 0; c < m; ++c) {
-        if (!(lo[c].w == 0.f)) continue;                  // special cylinders are not in the tree
-        order[n++] = c;
-        const float cx = 0.5f * (lo[c].x + hi[c].x), cy = 0.5f * (lo[c].y + hi[c].y), cz = 0.5f * (lo[c].z + hi[c].z);
-        clo[0] = std::min(clo[0], cx); clo[1] = std::min(clo[1], cy); clo[2] = std::min(clo[2], cz);
-        chi[0] = std::max(chi[0], cx); chi[1] = std::max(chi[1], cy); chi[2] = std::max(chi[2], cz);
-    }
-    if (n == 0) return TM_OK;
-    std::vector<uint64_t> keyed(n);
+    if (n <= 0) return TM_OK;
+    int depth = 0;                                              // leaves live at depth <= `depth`
+    while (((n + (1 << depth) - 1) >> depth) > BVH_LEAF) ++depth;
+    const int slots = 2 << depth;                               // heap slots 1 .. 2^(depth+1) - 1
     float scale[3];
-    for (int k = 0; k < 3; ++k) scale[k] = chi[k] > clo[k] ? 1023.999f / (chi[k] - clo[k]) : 0.f;
-    for (int i = 0; i < n; ++i) {
-        const int c = order[i];
-        const uint32_t qx = static_cast<uint32_t>((0.5f * (lo[c].x + hi[c].x) - clo[0]) * scale[0]);
-        const uint32_t qy = static_cast<uint32_t>((0.5f * (lo[c].y + hi[c].y) - clo[1]) * scale[1]);
-        const uint32_t qz = static_cast<uint32_t>((0.5f * (lo[c].z + hi[c].z) - clo[2]) * scale[2]);
-        const uint32_t code = expand10(qx) | (expand10(qy) << 1) | (expand10(qz) << 2);
-        keyed[i] = (static_cast<uint64_t>(code) << 32) | static_cast<uint32_t>(c);
-    }
-    // LSD radix sort of the 30-bit codes, 3 passes of 10 bits (stable: ties keep ascending rows); std::sort costs 3 ms at 50k
-    {
-        std::vector<uint64_t> tmp(n);
-        uint64_t *src = keyed.data(), *dst = tmp.data();
-        for (int pass = 0; pass < 3; ++pass) {
-            const int shift = 32 + 10 * pass;
-            uint32_t hist[1025] = {0};
-            for (int i = 0; i < n; ++i) ++hist[((src[i] >> shift) & 1023u) + 1];
-            for (int b = 0; b < 1024; ++b) hist[b + 1] += hist[b];
-            for (int i = 0; i < n; ++i) dst[hist[(src[i] >> shift) & 1023u]++] = src[i];
-            std::swap(src, dst);
-        }
-        if (src != keyed.data()) std::memcpy(keyed.data(), src, sizeof(uint64_t) * n);
-    }
-    for (int i = 0; i < n; ++i) order[i] = static_cast<int32_t>(static_cast<uint32_t>(keyed[i]));
-    BuildCtx cx;
-    cx.lo = lo_p; cx.hi = hi_p; cx.order = order;
-    cx.nodes = nodes_p; cx.n_nodes = 0;
-    float rlo[3], rhi[3];
-    h->bvh_root = build_range(cx, 0, n, rlo, rhi);
-    h->bvh_count = n;
-    const size_t nnodes = std::max<size_t>(static_cast<size_t>(cx.n_nodes), 1);
-    TM_CUDA(h, h->bvh_nodes.ensure(sizeof(BvhNode) * nnodes));
-    TM_CUDA(h, h->bvh_rows.ensure(sizeof(int32_t) * n));
-    TM_CUDA(h, h->bvh_leafAB.ensure(sizeof(float4) * 2 * n));
-    if (cx.n_nodes > 0)
-        TM_CUDA(h, cudaMemcpyAsync(h->bvh_nodes.p, nodes_p, sizeof(BvhNode) * cx.n_nodes, cudaMemcpyHostToDevice, stream));
-    TM_CUDA(h, cudaMemcpyAsync(h->bvh_rows.p, order, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream));
+    for (int k = 0; k < 3; ++k) scale[k] = hi[k] > lo[k] ? 1023.999f / (hi[k] - lo[k]) : 0.f;
+
+    size_t tmp_bytes = 0;
+    unsigned long long *nokeys = nullptr;
+    TM_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, nokeys, nokeys, m, 32, 64, stream));
+    const size_t key_bytes = (sizeof(unsigned long long) * static_cast<size_t>(m) + 255) & ~static_cast<size_t>(255);
+    const size_t slot_bytes = (sizeof(BvhSlot) * static_cast<size_t>(slots) + 255) & ~static_cast<size_t>(255);
+    const size_t arr_bytes = (sizeof(int) * static_cast<size_t>(slots) + 255) & ~static_cast<size_t>(255);
+    TM_CUDA(h, h->bvh_scratch.ensure(2 * key_bytes + slot_bytes + arr_bytes + tmp_bytes));
+    unsigned char *base = h->bvh_scratch.as<unsigned char>();
+    unsigned long long *keys_in = reinterpret_cast<unsigned long long *>(base);
+    unsigned long long *keys_out = reinterpret_cast<unsigned long long *>(base + key_bytes);
+    BvhSlot *scratch = reinterpret_cast<BvhSlot *>(base + 2 * key_bytes);
+    int *arrivals = reinterpret_cast<int *>(base + 2 * key_bytes + slot_bytes);
+    void *cub_tmp = base + 2 * key_bytes + slot_bytes + arr_bytes;
+    TM_CUDA(h, h->bvh_nodes.ensure(sizeof(BvhNode) * static_cast<size_t>(slots)));
+    TM_CUDA(h, h->bvh_rows.ensure(sizeof(int32_t) * static_cast<size_t>(n)));
+    TM_CUDA(h, h->bvh_leafAB.ensure(sizeof(float4) * 2 * static_cast<size_t>(n)));
+
+    bvh_key_kernel<<<(m + 255) / 256, 256, 0, stream>>>(h->boxlo.as<float4>(), h->boxhi.as<float4>(), m, lo[0], lo[1], lo[2], scale[0],
+                                                       scale[1], scale[2], keys_in);
+    TM_KCHECK(h, stream, "bvh_key_kernel");
+    // stable sort on the code bits only: rows stay ascending among equal codes, special cylinders (all ones) end up last
+    TM_CUDA(h, cub::DeviceRadixSort::SortKeys(cub_tmp, tmp_bytes, keys_in, keys_out, m, 32, 64, stream));
+    TM_CUDA(h, cudaMemsetAsync(arrivals, 0, sizeof(int) * static_cast<size_t>(slots), stream));
+    const int threads = std::max(n, slots);
+    bvh_build_kernel<<<(threads + 255) / 256, 256, 0, stream>>>(keys_out, h->boxlo.as<float4>(), h->boxhi.as<float4>(), n, slots,
+                                                                h->bvh_rows.as<int32_t>(), scratch, arrivals, h->bvh_nodes.as<BvhNode>());
+    TM_KCHECK(h, stream, "bvh_build_kernel");
     bvh_leaf_gather_kernel<<<(n + 255) / 256, 256, 0, stream>>>(h->bvh_rows.as<int32_t>(), n, h->recAB.as<float4>(),
                                                               h->bvh_leafAB.as<float4>());
     TM_KCHECK(h, stream, "bvh_leaf_gather_kernel");
-    TM_CUDA(h, cudaStreamSynchronize(stream));            // the staging buffer is reused by the next build
+    h->bvh_root = n <= BVH_LEAF ? -1 - ((0 << 3) | (n - 1)) : 1;
+    h->bvh_count = n;
     return TM_OK;
 }
 

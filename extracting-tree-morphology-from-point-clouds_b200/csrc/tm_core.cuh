@@ -123,8 +123,7 @@ struct tm_handle {
     tmn::DevBuf bvh_rows;            // int32: cylinder row per leaf slot (Morton order)
     tmn::DevBuf bvh_leafAB;          // float4[2 x count]: records in leaf order
     int32_t bvh_root = 0, bvh_count = 0;
-    void *bvh_pinned = nullptr;      // host staging of the BVH build
-    size_t bvh_pinned_cap = 0;
+    tmn::DevBuf bvh_scratch;         // build-time scratch of the BVH (sort keys, per-slot boxes, counters)
     uint64_t index_entries = 0;
     uint32_t voxels_with_tiles = 0;  // voxels within D_max of some cylinder (density estimate for the point sort)
 
@@ -246,7 +245,7 @@ struct SmallArgs {
 int run_proximity(tm_handle *h, const SmallArgs &a, bool guard, bool nfma, cudaStream_t st);
 int exclusive_scan_u32(tm_handle *h, const uint32_t *count, uint32_t n, uint32_t *start, cudaStream_t stream);
 // tm_bvh.cu
-int build_bvh(tm_handle *h, cudaStream_t stream);
+int build_bvh(tm_handle *h, cudaStream_t stream, int n_regular, const float *lo, const float *hi);
 int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst);
 // tm_grid.cu
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream);

@@ -598,9 +598,9 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     h->voxels_with_tiles = with_tiles;
     lap("tile sort");
     // (tile_keys is build-time scratch, kept for the next table: cudaFree + cudaMalloc cost more than the build's kernels)
-    rc = build_bvh(h, stream);
+    rc = build_bvh(h, stream, static_cast<int>(n_regular), lo, hi);
     if (rc != TM_OK) return rc;
-    lap("bvh (host)");
+    lap("bvh");
     h->have_grid = true;
     return TM_OK;
 }
