@@ -912,25 +912,44 @@ int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
         cyl[7 * c + 3] = end_host[3 * c];   cyl[7 * c + 4] = end_host[3 * c + 1];   cyl[7 * c + 5] = end_host[3 * c + 2];
         cyl[7 * c + 6] = radius_host[c];
     }
-    TM_CUDA(h, cudaMemcpyAsync(h->small_in.p, stage, idx_bytes + cyl_bytes, cudaMemcpyHostToDevice, st));
-
+    // This caller is latency-bound (thousands of calls per tree on a few thousand rows).  Up to 64k rows the kernel reads
+    // the staged rows / cylinders from the page-locked block itself and writes its results into page-locked memory (the
+    // host pointers are device-accessible): ONE launch and one synchronisation per call instead of copy + launch + up to
+    // three copies into pageable arrays.  Larger subsets go through device buffers with DMA copies.
+    const bool direct = n <= 65536 && getenv("TM_SMALL_STAGED") == nullptr;
     tmn::SmallArgs a;
     a.cloud = h->cloud_res.as<float>();
-    a.subset = subset_host ? h->small_in.as<int64_t>() : nullptr;
     a.n = n;
-    a.cyl = reinterpret_cast<const float *>(h->small_in.as<unsigned char>() + idx_bytes);
     a.m = static_cast<int>(m);
     a.axis_eps = axis_eps; a.atol = params->perp_atol; a.eps_norm = params->norm_eps; a.eps_flag = eps;
-    unsigned char *ob = h->small_out.as<unsigned char>();
+    unsigned char *ob;
+    if (direct) {
+        TM_CUDA(h, h->pinned_out[0].ensure(std::max<size_t>(static_cast<size_t>(n) * 9 + 16, 1 << 20)));
+        a.subset = subset_host ? reinterpret_cast<const int64_t *>(stage) : nullptr;
+        a.cyl = cyl;
+        ob = static_cast<unsigned char *>(h->pinned_out[0].p);
+    } else {
+        TM_CUDA(h, cudaMemcpyAsync(h->small_in.p, stage, idx_bytes + cyl_bytes, cudaMemcpyHostToDevice, st));
+        a.subset = subset_host ? h->small_in.as<int64_t>() : nullptr;
+        a.cyl = reinterpret_cast<const float *>(h->small_in.as<unsigned char>() + idx_bytes);
+        ob = h->small_out.as<unsigned char>();
+    }
     a.dist = out_dist_host ? reinterpret_cast<float *>(ob) : nullptr;
     a.index = out_index_host ? reinterpret_cast<int32_t *>(ob + 4 * static_cast<size_t>(n)) : nullptr;
     a.flags = out_flags_host ? ob + 8 * static_cast<size_t>(n) : nullptr;
     rc = tmn::run_proximity(h, a, params->norm_eps > 0.f, params->norm_fma != 0, st);
     if (rc != TM_OK) return rc;
-    if (out_dist_host) TM_CUDA(h, cudaMemcpyAsync(out_dist_host, a.dist, 4 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
-    if (out_index_host) TM_CUDA(h, cudaMemcpyAsync(out_index_host, a.index, 4 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
-    if (out_flags_host) TM_CUDA(h, cudaMemcpyAsync(out_flags_host, a.flags, static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
-    TM_CUDA(h, cudaStreamSynchronize(st));
+    if (direct) {
+        TM_CUDA(h, cudaStreamSynchronize(st));
+        if (out_dist_host) memcpy(out_dist_host, a.dist, 4 * static_cast<size_t>(n));
+        if (out_index_host) memcpy(out_index_host, a.index, 4 * static_cast<size_t>(n));
+        if (out_flags_host) memcpy(out_flags_host, a.flags, static_cast<size_t>(n));
+    } else {
+        if (out_dist_host) TM_CUDA(h, cudaMemcpyAsync(out_dist_host, a.dist, 4 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+        if (out_index_host) TM_CUDA(h, cudaMemcpyAsync(out_index_host, a.index, 4 * static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+        if (out_flags_host) TM_CUDA(h, cudaMemcpyAsync(out_flags_host, a.flags, static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+        TM_CUDA(h, cudaStreamSynchronize(st));
+    }
     h->stats = tm_stats{};
     h->stats.mode_used = TM_MODE_BRUTE;
     h->stats.pairs_evaluated = static_cast<uint64_t>(n) * static_cast<uint64_t>(m);
