@@ -58,7 +58,7 @@ noise_cloud_kernel(const double *__restrict__ rec, const int64_t *__restrict__ f
     const int64_t last = min(base + NOISE_THREADS, n) - 1;
     if (threadIdx.x < 2) {
         // owner of the block's first / last point: largest c with first[c] <= g  (empty cylinders are skipped by the <=)
-        const int64_t g = point0 + (threadIdx.x == 0 ? base : last);
+        const int64_t g = min(point0 + (threadIdx.x == 0 ? base : last), first[m] - 1);
         int64_t lo = 0, hi = m;                                 // first[lo] <= g < first[hi]
         while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
@@ -67,7 +67,11 @@ noise_cloud_kernel(const double *__restrict__ rec, const int64_t *__restrict__ f
         range[threadIdx.x] = lo;
     }
     __syncthreads();
-    if (i < n) {
+    if (i < n && point0 + i >= first[m]) {
+        // a row past the end of the cloud (the caller asked for more rows than the plan holds): NaN, not another point
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        rows[threadIdx.x * 3] = rows[threadIdx.x * 3 + 1] = rows[threadIdx.x * 3 + 2] = nan;
+    } else if (i < n) {
         const int64_t g = point0 + i;                           // global point number: the Philox counter
         int64_t lo = range[0], hi = range[1] + 1;
         while (hi - lo > 1) {

@@ -220,7 +220,8 @@ int tm_radius_count(tm_handle *h, const double *pts, int64_t n, int64_t row_stri
  *     rows are split over calls or ranks;
  *   all three given (DEVICE (n,) float64, row i of this call): used as is — this is how the parity tests replay the
  *     reference's own Mersenne-Twister draws.
- * float64 arithmetic in the reference's order.  n == 0 is a no-op; m == 0 with n > 0 is TM_ERR_NO_CYLINDERS.
+ * float64 arithmetic in the reference's order.  n == 0 is a no-op; m == 0 with n > 0 is TM_ERR_NO_CYLINDERS; rows at or
+ * beyond first_point[m] come back as NaN.
  */
 int tm_noise_cloud(tm_handle *h, const double *cyl_rec, const int64_t *first_point, int64_t m, int64_t n, int64_t point0,
                    uint64_t seed, const double *theta, const double *z, const double *noise,

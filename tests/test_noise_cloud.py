@@ -190,6 +190,10 @@ def test_edge_cases():
     with pytest.raises(IndexError):                              # rows asked of an empty table (TM_ERR_NO_CYLINDERS)
         eng.noise_cloud(rec, first, n=4)
     hp = N.cylinder_plan(df)
+    rec_d, first_d = torch.from_numpy(hp.records).cuda(), torch.from_numpy(hp.first_point).cuda()
+    over = eng.noise_cloud(rec_d, first_d, n=300, point0=hp.n_points - 100, seed=1).cpu().numpy()     # 200 rows past the end
+    assert np.isfinite(over[:100]).all() and np.isnan(over[100:]).all()
+    assert np.array_equal(over[:100], eng.noise_cloud(rec_d, first_d, seed=1).cpu().numpy()[-100:])
     with pytest.raises(ValueError):
         eng.noise_cloud(torch.from_numpy(hp.records).cuda(), torch.from_numpy(hp.first_point).cuda(), n=10,
                         variates=(np.zeros(10), np.zeros(10), np.zeros(9)))
