@@ -521,3 +521,28 @@ def test_largest_table_of_the_sweep(eng, vn):
     ora = oracle_label(case, pts[osub])
     got = {k: full[k][torch.tensor(osub, device=dev)].cpu().numpy() for k in ("index", "id", "dist", "offset")}
     assert_parity(got, ora, f"{n}x{m}/{vn} vs oracle", require_bitwise=True)
+
+
+@pytest.mark.parametrize("m", [1, 2, 4, 5, 7, 8, 9, 16, 17, 31, 33, 64, 65, 129, 1000, 4097])
+def test_tree_search_for_every_tree_shape(eng, m):
+    """The bounding-volume hierarchy is built on the device from the table size alone (implicit split-in-the-middle tree,
+    leaves of <= 4): root-is-a-leaf, odd splits and leaves at two depths must all give the exhaustive answer.  Half of the
+    points lie far outside the voxel grid (tree search only), half are clutter inside it."""
+    rng = np.random.default_rng(1000 + m)
+    case = make_case(max(m, 1), 4, seed=200 + m, variant="A" if m % 2 else "B")
+    lo = case["start"].min(0) - 1.0
+    hi = case["start"].max(0) + 1.0
+    n = 6000
+    pts = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    pts[: n // 2] += (rng.normal(0, 1, (n // 2, 3)) * 40.0 + 60.0).astype(np.float32)
+    case["points"] = pts
+    _install(eng, case)
+    with np.errstate(all="ignore"):
+        got = _label(eng, case, pts, "grid", cell_size=0.25 if m > 4 else 0.0)
+        if eng.stats()["mode_used"] == 2:
+            assert eng.stats()["points_tree"] > 0
+        want = _label(eng, case, pts, "brute")
+    for k in ("index", "id", "dist", "offset"):
+        assert_same_bits(got[k], want[k], f"m={m}: {k}")
+    ora = oracle_label(case, pts[:: 10])
+    assert_parity({k: v[:: 10] for k, v in got.items()}, ora, f"tree shapes m={m}", require_bitwise=True)
