@@ -15,3 +15,49 @@ def test_result_array_falls_back_to_pageable(monkeypatch):
         assert out.shape == (1000, 7) and out.dtype == np.float64 and out.flags.c_contiguous and out.flags.writeable
     assert api.Engine._new_records(0).shape == (0, 7)
     assert api._pinned_live >= 0
+
+
+def test_implicit_tree_numbering_used_by_the_device_bvh_build():
+    """csrc/tm_bvh.cu builds the hierarchy without recursion: node = binary-heap slot, range of a slot = follow the bits of
+    the slot number from the root splitting count -> (count // 2, count - count // 2), leaf when count <= 4, and the slot
+    array is sized 2 << depth with depth the first level where ceil(n / 2^depth) <= 4.  This mirrors those formulas in
+    Python and checks them against the plain recursive split for every table size up to 3000 and a few large ones."""
+    LEAF = 4
+
+    def slot_range(slot, n):
+        first, count = 0, n
+        depth = slot.bit_length() - 1
+        for b in range(depth - 1, -1, -1):
+            if count <= LEAF:
+                return None                                  # an ancestor is a leaf
+            half = count // 2
+            if (slot >> b) & 1:
+                first, count = first + half, count - half
+            else:
+                count = half
+        return first, count
+
+    def recurse(slot, first, count, out):
+        out[slot] = (first, count)
+        if count > LEAF:
+            half = count // 2
+            recurse(2 * slot, first, half, out)
+            recurse(2 * slot + 1, first + half, count - half, out)
+
+    for n in list(range(1, 3001)) + [50_000, 199_999, 200_000, 1_000_003]:
+        depth = 0
+        while ((n + (1 << depth) - 1) >> depth) > LEAF:
+            depth += 1
+        slots = 2 << depth
+        want = {}
+        recurse(1, 0, n, want)
+        assert max(want) < slots, n
+        leaves = sorted((f, c) for f, c in want.values() if c <= LEAF)
+        assert leaves[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(leaves, leaves[1:])) and sum(c for _, c in leaves) == n
+        check = want if n <= 3000 else {s: want[s] for s in list(want)[:: max(1, len(want) // 500)]}
+        for slot, rng in check.items():
+            assert slot_range(slot, n) == rng, (n, slot)
+        if n <= 300:                                          # slots that do not exist are recognised as such
+            for slot in range(1, slots):
+                got = slot_range(slot, n)
+                assert (got is None) == (slot not in want), (n, slot)
