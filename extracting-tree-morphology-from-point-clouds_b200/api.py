@@ -76,7 +76,7 @@ class Engine:
         B.check(self._lib, None, self._lib.tm_create(dev.index, ctypes.byref(h)))
         self._h = h
         self.m = 0
-        self._keep: tuple = ()
+        self.installs = 0          # bumped by every set_cylinders: callers that cache "my table is installed" compare it
 
     # -- lifetime ----------------------------------------------------------------------------
     def close(self) -> None:
@@ -135,6 +135,7 @@ class Engine:
             _ptr(length), length.stride(0) if m else 1, _ptr(radius), radius.stride(0) if m else 1,
             _ptr(ids), (ids.stride(0) if m else 1) if ids is not None else 1, m, _stream_ptr(self.device)))
         self.m = m
+        self.installs += 1
 
     # -- point side --------------------------------------------------------------------------
     def _params(self, variant: Variant, move_to_mantle: bool, norm_fma: bool, mode: str, cell_size: float) -> B.TmParams:

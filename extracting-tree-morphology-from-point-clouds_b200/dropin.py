@@ -13,7 +13,10 @@ from . import api
 
 QSM_COLUMNS = ("startX", "startY", "startZ", "endX", "endY", "endZ", "radius", "ID")
 
-_table_key: dict[int, tuple] = {}          # device index -> identity of the installed cylinder tensors
+# device index -> (the caller's cylinder tensor OBJECTS, their _version counters, the engine's install counter).
+# The objects are held strongly: an address can be recycled by the caching allocator the moment its tensor dies, so
+# only "the very same live tensor objects, unmodified, and nobody installed another table since" skips the install.
+_table_key: dict[int, tuple] = {}
 
 
 def _cuda_device(device) -> torch.device:
@@ -26,8 +29,14 @@ def _cuda_device(device) -> torch.device:
     return dev
 
 
-def _identity(*tensors) -> tuple:
-    return tuple((t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version) for t in tensors)
+def _same_table(dev_index: int, eng, given: tuple) -> bool:
+    held = _table_key.get(dev_index)
+    if held is None:
+        return False
+    objs, versions, installs = held
+    return (installs == eng.installs and len(objs) == len(given)
+            and all(a is b for a, b in zip(objs, given))
+            and all(t._version == v for t, v in zip(given, versions)))
 
 
 def closest_cylinder(points, start, radius, axis_length, axis_unit, IDs, device, variant: api.Variant,
@@ -39,18 +48,23 @@ def closest_cylinder(points, start, radius, axis_length, axis_unit, IDs, device,
     """
     dev = _cuda_device(device)
     eng = api.get_engine(dev)
+    given = (start, radius, axis_length, axis_unit, IDs)
     cyl = []
-    for t, dt in ((start, torch.float32), (radius, torch.float32), (axis_length, torch.float32),
-                  (axis_unit, torch.float32), (IDs, torch.int32)):
+    for t, dt in zip(given, (torch.float32, torch.float32, torch.float32, torch.float32, torch.int32)):
         t = torch.as_tensor(t)
         if t.device != dev or t.dtype != dt:
             t = t.to(device=dev, dtype=dt)
         cyl.append(t)
     start_t, radius_t, length_t, unit_t, ids_t = cyl
-    key = _identity(*cyl)
-    if _table_key.get(dev.index) != key:
+    # the install is skipped only for the caller's own tensor objects (label_clouds-style loops pass the same five
+    # tensors for every batch); anything converted on the way in, or not a tensor, is installed again
+    reusable = all(isinstance(g, torch.Tensor) and g is c for g, c in zip(given, cyl))
+    if not (reusable and _same_table(dev.index, eng, given)):
         eng.set_cylinders(start_t, radius_t, length_t, unit_t, ids_t)
-        _table_key[dev.index] = key
+        if reusable:
+            _table_key[dev.index] = (given, tuple(t._version for t in given), eng.installs)
+        else:
+            _table_key.pop(dev.index, None)
     m = start_t.shape[0]
     # ATen rounds norm() differently for a contiguous xyz axis (C-ordered tensors, or M == 1) than for
     # the Fortran-ordered tensors the DataFrame path produces; mirror whichever the caller's layout implies.

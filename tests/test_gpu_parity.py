@@ -546,3 +546,95 @@ def test_tree_search_for_every_tree_shape(eng, m):
         assert_same_bits(got[k], want[k], f"m={m}: {k}")
     ora = oracle_label(case, pts[:: 10])
     assert_parity({k: v[:: 10] for k, v in got.items()}, ora, f"tree shapes m={m}", require_bitwise=True)
+
+
+# ---- table cache of the kernel-level drop-in --------------------------------------------------------------
+
+@pytest.mark.parametrize("vn", ["A", "B"])
+def test_fresh_tables_of_the_same_shape_are_reinstalled(vn):
+    """closest_cylinder_cuda_batch called the way cylinder_proximity_based_segmentation calls it (QSMFittingDepthFirst.py:
+    1079-1081): brand-new cylinder tensors of the SAME shape for every call, the previous ones already freed — the caching
+    allocator hands their addresses out again.  Every call must be answered against the table it was given."""
+    mod = L if vn == "A" else P
+    dev = torch.device("cuda")
+    var = _oracle.VARIANTS[vn]
+    pts = None
+    for rep in range(6):
+        case = make_case(300, 2000, seed=40 + rep, variant=vn)
+        if pts is None:
+            pts = case["points"]
+        tabs = [torch.tensor(case[k], device=dev) for k in ("start", "radius", "length", "unit", "ids")]
+        ids, dist, off = mod.closest_cylinder_cuda_batch(pts, *tabs, dev)
+        # the same five tensor objects again: the table may be reused, the answer is the same
+        ids2, dist2, off2 = mod.closest_cylinder_cuda_batch(pts, *tabs, dev)
+        assert_same_bits(ids, ids2), assert_same_bits(dist, dist2)
+        ora = _oracle.label(pts, case["start"], case["radius"], case["length"], case["unit"], case["ids"], var, norm_fma=True)
+        assert_same_bits(ids, ora["id"], f"rep {rep}: ids")
+        assert_same_bits(dist, ora["dist"], f"rep {rep}: distances")
+        assert_same_bits(off, ora["offset"], f"rep {rep}: offsets")
+        # in-place edit of an installed tensor: must be noticed as well
+        tabs[1].mul_(1.5)
+        ids3, dist3, _ = mod.closest_cylinder_cuda_batch(pts, *tabs, dev)
+        ora3 = _oracle.label(pts, case["start"], case["radius"] * np.float32(1.5), case["length"], case["unit"], case["ids"], var,
+                             norm_fma=True)
+        assert_same_bits(ids3, ora3["id"], f"rep {rep}: ids after the in-place edit")
+        assert_same_bits(dist3, ora3["dist"], f"rep {rep}: distances after the in-place edit")
+        del tabs
+        gc.collect()
+
+
+# ---- BASELINE.json configs[3]: projection of model-corrected points, full size -----------------------------------
+
+def test_config4_projection_5m_points_50k_cylinders():
+    """5M PointTransformerV3-style points (N(0, 1 cm) residuals) x 50k cylinders through the Projection drop-in
+    (Modules/Projection.py:117-144 signature; pageable float64 cloud in, (N,7) float64 out): equal to the oracle on a 20k-row
+    sample, to the exhaustive kernel on another, xyz columns are the input's own float64 values."""
+    from treemorph_b200 import synth
+    n, m = 5_000_000, 50_000
+    q = synth.random_qsm(m, seed=1)
+    pts32 = synth.sample_points(q, n, seed=5, noise="model")
+    cloud = pts32.astype(np.float64)
+    out = P.generate_offset_cloud_cuda_batched(cloud, pd.DataFrame(q), torch.device("cuda"))
+    assert out.shape == (n, 7) and out.dtype == np.float64
+    assert np.array_equal(out[:, :3], cloud)
+    rng = np.random.default_rng(9)
+    rows = np.sort(rng.choice(n, 20_000, replace=False))
+    ora = _oracle.label_cloud(cloud[rows], q, _oracle.VARIANT_B)
+    assert_same_bits(out[rows], ora, "configs[3] vs oracle")
+    # exhaustive kernel on the device for a second, larger sample
+    rows2 = np.sort(rng.choice(n, 100_000, replace=False))
+    e = api.get_engine(torch.device("cuda"))
+    res = e.label(torch.tensor(pts32[rows2], device=e.device), api.VARIANT_B, mode="brute", want=("id", "offset"))
+    assert np.array_equal(res["id"].cpu().numpy().astype(np.float64), out[rows2, 6])
+    assert_same_bits(res["offset"].cpu().numpy().astype(np.float64), out[rows2, 3:6], "configs[3] vs exhaustive")
+
+
+def test_full_size_properties_variant_b(eng):
+    """configs[2] size in variant B (Projection.py arithmetic: atol 1e-3, guarded norms): grid == exhaustive == oracle on
+    subsets, invariant under permutation."""
+    from treemorph_b200 import synth
+    n, m = 10_000_000, 50_000
+    q = synth.random_qsm(m, seed=1)
+    pts = synth.sample_points(q, n, seed=2)
+    var = _oracle.VARIANT_B
+    start, radius, length, unit, ids = synth.cylinder_arrays(q, var.axis_eps)
+    case = {"start": start, "radius": radius, "length": length, "unit": unit, "ids": ids, "variant": var, "points": pts}
+    _install(eng, case)
+    dev = eng.device
+    dpts = torch.tensor(pts, device=dev)
+    full = eng.label(dpts, api.VARIANT_B, mode="grid", want=("index", "id", "dist", "offset"))
+    rng = np.random.default_rng(4)
+    sub = torch.tensor(rng.choice(n, 20_000, replace=False), device=dev)
+    brute = eng.label(dpts[sub], api.VARIANT_B, mode="brute", want=("index", "id", "dist", "offset"))
+    for k in ("index", "id", "dist", "offset"):
+        a, b = full[k][sub], brute[k]
+        same = (a == b) | (torch.isnan(a) & torch.isnan(b)) if a.dtype.is_floating_point else (a == b)
+        assert bool(same.all()), f"{k}: grid != exhaustive on the subset"
+    osub = sub[:4000].cpu().numpy()
+    ora = oracle_label(case, pts[osub])
+    got = {k: full[k][sub[:4000]].cpu().numpy() for k in ("index", "id", "dist", "offset")}
+    assert_parity(got, ora, "10M x 50k variant B vs oracle", require_bitwise=True)
+    perm = torch.randperm(n, device=dev)
+    again = eng.label(dpts[perm], api.VARIANT_B, mode="grid", want=("index", "dist"))
+    assert bool((again["index"] == full["index"][perm]).all())
+    assert bool((again["dist"] == full["dist"][perm]).all())

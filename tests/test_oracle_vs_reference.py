@@ -40,3 +40,19 @@ def test_contiguous_tensor_path_bit_exact(vn):
     assert_same_bits(o["id"], rid, "ids")
     assert_same_bits(o["dist"], rdist, "distances")
     assert_same_bits(o["offset"], roff, "offsets")
+
+
+@pytest.mark.parametrize("vn", ["A", "B"])
+def test_torch_mirror_is_the_reference_chain(vn):
+    """oracle/torch_mirror.py (the comparator that runs on the GPU box, where the reference cannot travel) issues the
+    reference's own ATen calls: on the CPU it must reproduce the live reference bit for bit."""
+    import torch
+    from oracle import torch_mirror
+    synth = _synth()
+    var = oracle.VARIANTS[vn]
+    q = synth.random_qsm(500, seed=121)
+    pts = synth.sample_points(q, 2048 + 5, seed=122)
+    ref = ref_harness.run_cloud(vn, pts, synth.qsm_dataframe(q), batch_size=1024)
+    got = torch_mirror.label(pts, q, torch.device("cpu"), var.perp_atol, var.norm_eps, var.axis_eps, fortran=True)
+    assert_same_bits(got["offset"].astype(np.float64), ref[:, 3:6], f"variant {vn}: offsets")
+    assert_same_bits(got["id"].astype(np.float64), ref[:, 6], f"variant {vn}: ids")
