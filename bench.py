@@ -6,12 +6,20 @@
 
 Workload (config.workload): BASELINE.json configs[2] — a noise-augmented plot, 10M NoiseDataGeneration-style
 points against a 50k-cylinder QSM (10 synthetic trees), variant A (label generation).  One "step" labels the
-whole cloud once: device-resident fp32 points in, device-resident (index, id, distance, offset) out, including
+cloud once: device-resident fp32 points in, device-resident (index, id, distance, offset) out, including
 everything that depends on the points (voxel binning / sort, tile kernel, ring / tree search, winner epilogue in input
-order); the per-table voxel index and BVH are built once before the timed region (reported as setup_ms).  The e2e leg
-goes through the host API: pinned fp32 cloud in, (N,7) float64 records out, copies inside the timed region.  With N GPUs every rank labels its own
-10M-point cloud against the same table, which rank 0 broadcasts once over NCCL (weak scaling, no data-path
-collective).  Prints ONE JSON line on rank 0.
+order); the per-table voxel index and BVH are built once before the timed region (reported as setup_ms).
+
+With N GPUs (default --scaling strong, north_star's split) the ONE 10M-point plot is sharded: rank 0 broadcasts the
+cylinder table once over NCCL, rank r labels the contiguous rows shard_bounds(10M, N, r), there is no data-path
+collective, `value` = 10M points / the slowest rank's step time.  The same run also reports the weak-scaling figure
+(every rank labels a full copy, key "weak") and checks on the hardware that the sharded rows, gathered over NCCL, are
+bit-identical to the single-GPU labelling (key "sharded_parity").  --scaling weak gives every rank its own 10M points.
+
+`e2e` goes through the call a user of the reference makes: LabelGenerationCuda.generate_offset_cloud_cuda_batched(
+float64 pageable cloud, DataFrame, device) -> (N,7) float64 records, table install and every copy inside the timed
+region; `e2e_pinned` is Engine.label_cloud_host on page-locked buffers with the table resident.  Prints ONE JSON line
+on rank 0.
 
 Timing: CUDA events on the launching stream around every step, L2 flushed between steps (256 MiB write),
 barrier + synchronize on both sides of the timed loop, max over ranks.
@@ -37,9 +45,6 @@ METRIC = "points/sec nearest-cylinder label+offset"
 UNIT = "points/s"
 OPS_PER_PAIR = 81                 # fp32 lane-ops per evaluated pair in reference order
 BYTES_PER_POINT = 36              # compulsory HBM traffic per point: 12 B xyz in + 24 B index/id/dist/offset out
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-call kernel, from the committed ncu --set full capture
-# of THIS command at the default workload (profiles/r01h_grid_kernels.md); null for any other workload
-NCU_DRAM_BYTES = {"evaluate": 346.81e6, "bin": 128.54e6, "scatter": 281.17e6, "epilogue": 314.56e6, "tree": 7.93e6}
 
 
 def load_peaks():
@@ -196,6 +201,30 @@ def reference_arm(args):
     return 0
 
 
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-call kernel at the default workload, from the
+    newest committed ncu --set full capture (profiles/*_dram_traffic.json, written by profiles/summarise.py together with the
+    git hash of the build that was profiled).  None when there is no capture."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        d = json.load(f)
+    d["source"] = f"profiles/{os.path.basename(files[-1])} (ncu --set full, bytes per launch, build {d.get('git', '?')})"
+    return d
+
+
+def stats_lane_ops(stats: dict) -> dict:
+    """FP32 lane-operations the counted work stands for: full evaluations in reference order (81) plus, when
+    the library reports them, the approximate-distance bounds of the tile kernel at their own documented count."""
+    pairs = stats["pairs_evaluated"]
+    bounds = stats.get("bound_tests", 0)
+    per_bound = stats.get("lane_ops_per_bound", 0)
+    return {"total": pairs * OPS_PER_PAIR + bounds * per_bound,
+            "detail": {"bound_tests": bounds, "lane_ops_per_bound": per_bound}}
+
 # ------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------------
@@ -211,6 +240,8 @@ def main():
     ap.add_argument("--cell", type=float, default=0.0)
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--cylinders", type=int, default=N_CYLINDERS)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: ONE plot of --points points sharded over the ranks (north_star); weak: --points per rank")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-brute", action="store_true", help="skip the exhaustive-kernel FP32 yard-stick")
     ap.add_argument("--skip-e2e", action="store_true", help="skip the host-API end-to-end leg (profiling runs)")
@@ -245,11 +276,15 @@ def main():
             os.close(saved_stdout)
 
     from treemorph_b200 import api, sharding, synth
-    eng = api.Engine(dev)
+    from treemorph_b200.PreProcessing import LabelGenerationCuda as dropin_A
+    eng = api.get_engine(dev)              # the engine the drop-in modules use
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
+    strong = args.scaling == "strong"
 
-    # ---- inputs: rank 0 owns the QSM and broadcasts the packed table once; every rank samples its own cloud
+    # ---- inputs: rank 0 owns the QSM and broadcasts the packed table once.  strong: ONE cloud, rank r owns the
+    #      contiguous rows shard_bounds(N, world, r) of it (LabelGenerationCuda.py:126-133 is the loop being sharded);
+    #      weak: every rank samples its own N-point cloud
     t_gen = time.time()
     qsm = synth.random_qsm(N_CYLINDERS, seed=1)
     table = None
@@ -267,13 +302,19 @@ def main():
     torch.cuda.synchronize()
     bcast_ms = e0.elapsed_time(e1)
     s_t, r_t, l_t, u_t, i_t = sharding.unpack_table(table)
-    pts_host = synth.sample_points(qsm, N_POINTS, seed=2 + rank)
-    pinned_in = torch.empty((N_POINTS, 3), dtype=torch.float32, pin_memory=True)
+    cloud_host = synth.sample_points(qsm, N_POINTS, seed=2 if strong else 2 + rank)
+    lo, hi = sharding.shard_bounds(N_POINTS, world, rank) if strong else (0, N_POINTS)
+    n_mine = hi - lo
+    pts_host = cloud_host[lo:hi]
+    total_points = N_POINTS if strong else world * N_POINTS
+    pinned_in = torch.empty((n_mine, 3), dtype=torch.float32, pin_memory=True)
     pinned_in.numpy()[:] = pts_host
     dpts = pinned_in.to(dev, non_blocking=True)
-    out = {"index": torch.empty(N_POINTS, dtype=torch.int32, device=dev), "id": torch.empty(N_POINTS, dtype=torch.int32, device=dev),
-           "dist": torch.empty(N_POINTS, dtype=torch.float32, device=dev),
-           "offset": torch.empty((N_POINTS, 3), dtype=torch.float32, device=dev)}
+
+    def new_out(n):
+        return {"index": torch.empty(n, dtype=torch.int32, device=dev), "id": torch.empty(n, dtype=torch.int32, device=dev),
+                "dist": torch.empty(n, dtype=torch.float32, device=dev), "offset": torch.empty((n, 3), dtype=torch.float32, device=dev)}
+    out = new_out(n_mine)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     gen_s = time.time() - t_gen
@@ -286,75 +327,134 @@ def main():
     torch.cuda.synchronize()
     setup_ms = e0.elapsed_time(e1)
 
-    def step():
-        eng.label(dpts, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=out, want=("index", "id", "dist", "offset"))
-
-    for _ in range(warmup):
-        flush.fill_(1)
-        step()
-    torch.cuda.synchronize()
-    stats = eng.stats()
+    def timed(points, result, n_steps, sample_clocks=False):
+        """warm-up, then n_steps steps: CUDA events on the launching stream, L2 flushed between steps, barrier + synchronize
+        on both sides, max over ranks.  Returns (total ms, clocks)."""
+        def one():
+            eng.label(points, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=result, want=("index", "id", "dist", "offset"))
+        for _ in range(warmup):
+            flush.fill_(1)
+            one()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if sample_clocks and rank == 0:
+            sampler.start()
+            time.sleep(0.05)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for a, b in evs:
+            flush.fill_(1)                      # evict the previous step's working set from the 126 MB L2
+            a.record()
+            one()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t1 = time.time()
+        clocks = sampler.stop(t0, t1) if (sample_clocks and rank == 0) else None
+        tm = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item()), clocks
 
     # ---- timed region
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.05)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.time()
-    for a, b in evs:
-        flush.fill_(1)                      # evict the previous step's working set from the 126 MB L2
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t1 = time.time()
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
+    total_ms, clocks = timed(dpts, out, steps, sample_clocks=True)
     ms_per_step = total_ms / steps
-    value = world * N_POINTS * steps / (total_ms * 1e-3)
+    value = total_points * steps / (total_ms * 1e-3)
+    stats = eng.stats()
 
-    # ---- per-phase device time of the dominant kernel (CUDA events inside the library, same stream)
+    # ---- per-phase device time (CUDA events inside the library, same stream)
     eng.set_profiling(True)
     phase_acc = {}
     for _ in range(3):
         flush.fill_(1)
-        step()
+        eng.label(dpts, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=out, want=("index", "id", "dist", "offset"))
         for k, v in eng.phase_ms().items():
             phase_acc.setdefault(k, []).append(v)
     eng.set_profiling(False)
     phases = {k: float(np.mean(v)) for k, v in phase_acc.items()}
     stats = eng.stats()
 
-    # ---- end to end through the public host API: pinned host cloud in, pinned (N,7) float64 records out
-    rec_pinned = torch.empty((N_POINTS, 7), dtype=torch.float64, pin_memory=True)
-    rec_np, cloud_np = rec_pinned.numpy(), pinned_in.numpy()
+    # ---- N > 1, strong: (i) the weak-scaling figure as an extra key (every rank labels the WHOLE cloud), which also gives
+    #      every rank the single-GPU answer; (ii) parity on hardware: the sharded rows, gathered over NCCL, against the
+    #      single-GPU labelling of the same cloud, bit for bit
+    weak = parity = None
+    if world > 1 and strong:
+        dfull = torch.as_tensor(cloud_host).to(dev)
+        out_full = new_out(N_POINTS)
+        wms, _ = timed(dfull, out_full, steps)
+        weak = {"value": world * N_POINTS * steps / (wms * 1e-3), "ms_per_step": wms / steps, "unit": UNIT,
+                "note": "every rank labels a full copy of the cloud (no sharding)"}
+        eng.label(dpts, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=out, want=("index", "id", "dist", "offset"))
+        width = -(-N_POINTS // world)
+        same = {}
+        for k in ("index", "id", "dist", "offset"):
+            mine = out[k].reshape(n_mine, -1)
+            pad = torch.zeros((width, mine.shape[1]), dtype=mine.dtype, device=dev)
+            pad[:n_mine] = mine
+            parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, parts, dst=0)
+            if rank == 0:
+                rows = torch.cat([p[: sharding.shard_bounds(N_POINTS, world, r)[1] - sharding.shard_bounds(N_POINTS, world, r)[0]]
+                                  for r, p in enumerate(parts)])
+                ref = out_full[k].reshape(N_POINTS, -1)
+                same[k] = bool(torch.equal(rows.view(torch.int32), ref.view(torch.int32)))      # bit patterns (NaN-safe)
+        if rank == 0:
+            parity = {"sharded_vs_single_gpu_bitwise": same, "rows": N_POINTS, "collective": "NCCL gather of every rank's rows to rank 0"}
+        del dfull, out_full
+        eng.label(dpts, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=out, want=("index", "id", "dist", "offset"))
+        stats = eng.stats()
+
+    # ---- end to end (i): the call a user of the reference makes — generate_offset_cloud_cuda_batched(float64 pageable
+    #      cloud, DataFrame, device) of the LabelGenerationCuda drop-in (reference :113), table install included
     e2e_steps = 0 if args.skip_e2e else max(2, min(steps, 5))
-    for _ in range(0 if args.skip_e2e else 2):
-        eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_POINTS * e2e_steps / float(te.item()) if e2e_steps else None
+    cloud64 = np.ascontiguousarray(pts_host, dtype=np.float64)            # pageable, the dtype np.load of a cloud file yields
+    qsm_df = synth.qsm_dataframe(qsm)
+    e2e_value = e2e_ok = None
+    rec = None
+    if e2e_steps:
+        for _ in range(2):
+            rec = dropin_A.generate_offset_cloud_cuda_batched(cloud64, qsm_df, dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            rec = dropin_A.generate_offset_cloud_cuda_batched(cloud64, qsm_df, dev)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = total_points * e2e_steps / float(te.item())
+        e2e_ok = bool((rec[:, 6] == out["id"].cpu().numpy()).all() and
+                      np.array_equal(rec[:, 3:6].astype(np.float32), out["offset"].cpu().numpy(), equal_nan=True)
+                      and np.array_equal(rec[:, :3], cloud64))
     pipe = eng.host_pipeline_info() if e2e_steps else {"d2h_bytes_per_point": 16, "host_threads": None}
-    e2e_ok = bool((rec_np[:1000, 6] == out["id"][:1000].cpu().numpy()).all()) if e2e_steps else None
+    del rec
+
+    # ---- end to end (ii): Engine.label_cloud_host on page-locked fp32 / page-locked records (table already installed)
+    eng.set_cylinders(s_t, r_t, l_t, u_t, i_t)
+    rec_pinned = torch.empty((n_mine, 7), dtype=torch.float64, pin_memory=True)
+    rec_np, cloud_np = rec_pinned.numpy(), pinned_in.numpy()
+    pinned_value = None
+    if e2e_steps:
+        for _ in range(2):
+            eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.label_cloud_host(cloud_np, api.VARIANT_A, mode=args.mode, cell_size=args.cell, out=rec_np)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        pinned_value = total_points * e2e_steps / float(te.item())
+    pipe_pinned = eng.host_pipeline_info() if e2e_steps else pipe
 
     if rank != 0:
         if world > 1:
@@ -366,32 +466,35 @@ def main():
     fp32_peak = eng.fp32_peak()
     dom = max(("evaluate", "tree", "exhaustive", "pending", "bin", "scatter", "scan", "epilogue"), key=lambda k: phases.get(k, 0.0))
     dom_ms = phases.get(dom, 0.0) or ms_per_step
-    achieved_gbs = BYTES_PER_POINT * N_POINTS / (dom_ms * 1e-3) / 1e9
+    achieved_gbs = BYTES_PER_POINT * n_mine / (dom_ms * 1e-3) / 1e9
     pairs = stats["pairs_evaluated"]
+    default_workload = (N_POINTS, N_CYLINDERS) == (10_000_000, 50_000) and args.mode == "grid" and n_mine == N_POINTS
+    traffic = load_ncu_traffic() if default_workload else None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak,
-                "traffic": NCU_DRAM_BYTES.get(dom) if (N_POINTS, N_CYLINDERS) == (10_000_000, 50_000) and args.mode == "grid" else None,
-                "traffic_source": "profiles/r01h_grid_kernels.md (ncu --set full, bytes per launch)", "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "traffic": (traffic or {}).get("kernels", {}).get(dom),
+                "traffic_source": (traffic or {}).get("source"), "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "kernel_ms": dom_ms,
                 "note": "dominant kernel is FP32-issue bound, not HBM bound: see fp32_roofline"}
-    fp32_roofline = {"kernel": dom, "pairs_evaluated": pairs, "lane_ops_per_pair": OPS_PER_PAIR,
-                     "achieved_lane_ops_per_s": pairs * OPS_PER_PAIR / (dom_ms * 1e-3), "peak_lane_ops_per_s": fp32_peak,
-                     "frac": pairs * OPS_PER_PAIR / (dom_ms * 1e-3) / fp32_peak if fp32_peak else None,
+    lane_ops = stats_lane_ops(stats)
+    fp32_roofline = {"kernel": dom, "pairs_evaluated": pairs, "lane_ops_per_pair": OPS_PER_PAIR, **lane_ops["detail"],
+                     "achieved_lane_ops_per_s": lane_ops["total"] / (dom_ms * 1e-3), "peak_lane_ops_per_s": fp32_peak,
+                     "frac": lane_ops["total"] / (dom_ms * 1e-3) / fp32_peak if fp32_peak else None,
                      "peak_source": "FFMA/FADD+FMUL chain probe in this run"}
 
     # whole step against HBM (compulsory bytes per point over the step), and the brute-force-equivalent pair
     # rate N*M/t -- a speed-up figure of the pruning, not a roofline fraction
-    step_gbs = BYTES_PER_POINT * N_POINTS / (ms_per_step * 1e-3) / 1e9
+    step_gbs = BYTES_PER_POINT * n_mine / (ms_per_step * 1e-3) / 1e9
     step_view = {"compulsory_bytes_per_point": BYTES_PER_POINT, "achieved_GBps": step_gbs, "hbm_frac": step_gbs / hbm_peak,
-                 "dram_bytes_all_kernels": sum(NCU_DRAM_BYTES.values()) if (N_POINTS, N_CYLINDERS) == (10_000_000, 50_000) and args.mode == "grid" else None,
-                 "brute_force_equivalent_pairs_per_s": float(N_POINTS) * N_CYLINDERS / (ms_per_step * 1e-3),
-                 "brute_force_equivalent_lane_ops_per_s": float(N_POINTS) * N_CYLINDERS * OPS_PER_PAIR / (ms_per_step * 1e-3),
-                 "pairs_evaluated_per_point": pairs / N_POINTS, "cull_tests_per_point": stats["cull_tests"] / N_POINTS}
+                 "dram_bytes_all_kernels": sum((traffic or {}).get("kernels", {}).values()) or None,
+                 "brute_force_equivalent_pairs_per_s": float(total_points) * N_CYLINDERS / (ms_per_step * 1e-3),
+                 "brute_force_equivalent_lane_ops_per_s": float(total_points) * N_CYLINDERS * OPS_PER_PAIR / (ms_per_step * 1e-3),
+                 "pairs_evaluated_per_point": pairs / n_mine, "cull_tests_per_point": stats["cull_tests"] / n_mine}
 
     # ---- exhaustive kernel as the FP32 yard-stick (pairs = N*M exactly)
     brute = None
     if not args.skip_brute:
-        nb = min(N_POINTS, 400_000)
+        nb = min(n_mine, 400_000)
         eng.label(dpts[:nb], api.VARIANT_A, mode="brute", want=("id",))
         torch.cuda.synchronize()
         e0.record()
@@ -415,24 +518,30 @@ def main():
                "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {host_threads()} threads "
                          f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
 
-    launches_per_step = {"grid": 11, "auto": 11, "brute": 2}[args.mode]     # count, 3 x scan, scatter, evaluate, ring, tree search, exhaustive, pending winners, epilogue
+    launches_per_step = stats.get("launches") or {"grid": 11, "auto": 11, "brute": 2}[args.mode]
+    shard_txt = (f"ONE plot of {N_POINTS} points sharded over {world} GPU(s) ({n_mine} rows on rank 0)" if strong
+                 else f"{N_POINTS} points per GPU")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{N_POINTS} points x {N_CYLINDERS} cylinders per GPU, variant A (label generation), "
+        "config": {"workload": f"{shard_txt} x {N_CYLINDERS} cylinders, variant A (label generation), "
                                f"random QSM plot + NoiseDataGeneration-style cloud", "mode": args.mode,
                    "cell_size_m": stats.get("cell_size"), "l2": "flushed between steps (256 MiB write)",
-                   "parallelism": f"points sharded x{world}, cylinder table broadcast once"},
+                   "parallelism": f"points sharded x{world}, cylinder table broadcast once over NCCL, no data-path collective"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * 12, "d2h_bytes_per_step": N_POINTS * pipe["d2h_bytes_per_point"],
-                "api": "Engine.label_cloud_host (tm_label_cloud_host): pinned fp32 cloud -> pinned (N,7) float64 records",
-                "host_assembly_threads": pipe["host_threads"],
-                "note": "with host_assembly_threads > 0 only {offset, id} (16 B/point) cross PCIe; the host workers write the 56 B records",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_mine * 24, "d2h_bytes_per_step": n_mine * pipe["d2h_bytes_per_point"],
+                "api": "PreProcessing.LabelGenerationCuda.generate_offset_cloud_cuda_batched(float64 pageable cloud, DataFrame, device) "
+                       "-> (N,7) float64 records; table install + voxel index build inside every call",
+                "host_assembly_threads": pipe["host_threads"], "bytes_are": "per rank",
                 "steps": e2e_steps, "checked": e2e_ok},
+        "e2e_pinned": {"value": pinned_value, "unit": UNIT, "h2d_bytes_per_step": n_mine * 12,
+                       "d2h_bytes_per_step": n_mine * pipe_pinned["d2h_bytes_per_point"],
+                       "api": "Engine.label_cloud_host (tm_label_cloud_host): page-locked fp32 cloud -> page-locked (N,7) float64 records, table resident",
+                       "host_assembly_threads": pipe_pinned["host_threads"]},
         "gpu_launches": launches_per_step * steps,
         "roofline": roofline, "fp32_roofline": fp32_roofline, "step_view": step_view, "brute_force_yardstick": brute,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "weak": weak, "sharded_parity": parity,
         "phases_ms": phases, "stats": stats, "setup_ms": setup_ms, "table_broadcast_ms": bcast_ms,
         "input_generation_s": gen_s,
     }
