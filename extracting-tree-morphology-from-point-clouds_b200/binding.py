@@ -13,7 +13,7 @@ from . import build as _build
 TM_OK, TM_ERR_INVALID, TM_ERR_NO_CYLINDERS, TM_ERR_CUDA, TM_ERR_NOMEM, TM_ERR_STATE = range(6)
 TM_MODE_AUTO, TM_MODE_BRUTE, TM_MODE_GRID = 0, 1, 2
 TM_F32, TM_F64 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 TM_PHASES = 9
 PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "tree", "exhaustive", "pending", "epilogue", "total")
 
@@ -31,7 +31,8 @@ class TmStats(ctypes.Structure):
                 ("points_brute", ctypes.c_uint64), ("index_entries", ctypes.c_uint64),
                 ("voxels_occupied", ctypes.c_uint32), ("work_items", ctypes.c_uint32),
                 ("mode_used", ctypes.c_uint32), ("cell_size", c_f32), ("reach", c_f32), ("near_reach", c_f32),
-                ("grid_dim", ctypes.c_uint32 * 3)]
+                ("grid_dim", ctypes.c_uint32 * 3), ("launches", ctypes.c_uint32), ("bound_tests", ctypes.c_uint64),
+                ("points_slow", ctypes.c_uint64), ("lane_ops_per_bound", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
     def as_dict(self) -> dict:
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "grid_dim"}

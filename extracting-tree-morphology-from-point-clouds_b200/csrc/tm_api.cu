@@ -311,7 +311,7 @@ int tm_destroy(tm_handle *h) {
     cudaDeviceSynchronize();
     tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->recAB, &h->cells, &h->bvh_nodes, &h->bvh_rows, &h->bvh_leafAB, &h->knn_cells, &h->knn_start, &h->knn_sorted, &h->knn_box, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->cell_count,
-                          &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileA, &h->tileB, &h->tileI, &h->items,
+                          &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileAB, &h->tileI, &h->items, &h->items2, &h->warp_item, &h->undecided,
                           &h->pend_idx, &h->brute_slots, &h->pend_done, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
                           &h->small_out, &h->bvh_scratch};
     for (auto *b : bufs) b->release();
@@ -982,6 +982,9 @@ int tm_get_stats(tm_handle *h, tm_stats *out) {
         s.index_entries = h->index_entries;
         s.voxels_occupied = d.voxels_occupied;
         s.work_items = d.work_items;
+        s.bound_tests += d.bound_tests;
+        s.points_slow += static_cast<uint64_t>(d.undecided_near) + d.undecided_far;
+        s.lane_ops_per_bound = tmn::LANE_OPS_PER_BOUND;
         s.cell_size = h->grid.h;
         s.reach = h->reach;
         s.near_reach = h->near;

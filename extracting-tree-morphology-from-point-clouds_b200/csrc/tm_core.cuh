@@ -74,13 +74,21 @@ struct DevStats {
     unsigned long long cull_tests;   // capsule lower-bound tests, all kernels
     unsigned long long points_binned;
     unsigned int voxels_occupied;
-    unsigned int work_items;
+    unsigned int work_items;         // occupied voxels with their tile descriptor (one item per voxel run)
     unsigned int pending;            // points the voxel-tile kernel could not certify (slots of pend_idx / keys)
     unsigned int n_brute;            // of those, points that need the exhaustive kernel (slots of brute_slots)
     unsigned int far_certified;      // points certified by the far part of their own tile (inside the tile kernel)
     unsigned int ring_certified;     // points certified by the ring search
     unsigned int bvh_cursor;         // next pending slot the tree search hands out
+    unsigned int lane_slots;         // (voxel, <= 2 points) lane slots of the tile kernel
+    unsigned int undecided_near;     // points the estimates left undecided but certified inside D_near (front of the list)
+    unsigned int undecided_far;      // points the estimates could not certify inside D_near (back of the list)
+    unsigned long long bound_tests;  // approximate-distance bounds computed by the tile kernel
 };
+
+// FP32 lane-operations of one closed-form distance estimate of the tile kernel (tm_grid.cu: bound_pair), counted the way
+// SURVEY.md A.6 counts the reference's 81: every add / sub / mul / fma / min / max / compare / select / rsqrt is one
+constexpr uint32_t LANE_OPS_PER_BOUND = 33;
 
 struct HostPool;                     // tm_api.cu
 
@@ -112,8 +120,8 @@ struct tm_handle {
     tmn::DevBuf cyl_cell_start;      // uint32[ncell_codes + 1]: first pool entry of each voxel's tile (multiple of 4)
     tmn::DevBuf cyl_cell_cnt;        // uint32[ncell_codes]: tile length
     tmn::DevBuf cyl_cell_near;       // uint32[ncell_codes]: length of the tile's near part (lower bound <= D_near)
-    tmn::DevBuf tileA, tileB, tileI; // tile pool: packed records + cylinder row of every (voxel, cylinder) entry,
-    tmn::DevBuf tileLB;              //            sorted per voxel by tileLB = lower bound of dist(voxel box, capsule)
+    tmn::DevBuf tileAB, tileI;       // tile pool: interleaved records {A, B} (one 32-byte sector) + cylinder row of every
+    tmn::DevBuf tileLB;              //            (voxel, cylinder) entry, sorted per voxel by tileLB = lower bound of dist(voxel box, capsule)
     tmn::DevBuf tile_keys;           // u64 per entry, build-time only: (bits(lower bound) << 32) | cylinder row
     tmn::DevBuf long_list;           // int32[]: cylinders whose dilated AABB spans too many voxels
     tmn::DevBuf special;             // int32[]: non-finite / non-unit cylinders, evaluated for every point
@@ -132,7 +140,10 @@ struct tm_handle {
     tmn::DevBuf cell_count, cell_start, block_sums;      // index build (cell_count / cell_start) and scan partials
     tmn::DevBuf cells;               // uint2 per voxel: {point count -> scatter cursor, first sorted point}
     tmn::DevBuf sorted_pts;          // float4 per point {x,y,z,bits(original row)}
-    tmn::DevBuf items;               // uint4 per work item
+    tmn::DevBuf items;               // uint4 per occupied voxel {tile offset, near length, first sorted point, point count}
+    tmn::DevBuf items2;              // uint2 per occupied voxel {far length, first lane slot}
+    tmn::DevBuf warp_item;           // uint32 per group of 32 lane slots: the item its first slot belongs to
+    tmn::DevBuf undecided;           // uint4 per point the estimates left undecided (exact kernel's work list)
     tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)
     tmn::DevBuf brute_slots;         // uint32 pending slots that need the exhaustive kernel
     tmn::DevBuf pend_done;           // uint8 per pending slot: 1 = final after the ring search

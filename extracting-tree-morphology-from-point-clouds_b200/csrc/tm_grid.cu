@@ -6,18 +6,19 @@
 //     The leading `near(V)` entries are those with lb <= D_near.
 //   per call:
 //     points --count/scan/scatter--> counting sort by voxel id (brick-Morton order) --> contiguous per-voxel runs
-//     evaluate:  one warp per (voxel, <= 64 points) work item.  The NEAR part of the voxel's tile is staged into shared
-//                memory with bulk async copies (double buffered, next item's tile prefetched).  For every tile entry
-//                each lane runs a 17-instruction capsule lower-bound test for its (up to) two points against the
-//                point's incumbent; surviving (point, entry) pairs are compacted into a per-warp queue (ballot +
-//                popc) and evaluated 32 at a time with the reference arithmetic, so the expensive evaluation always
-//                runs with full lanes.  Winners are merged with a 64-bit (distance, index) atomicMin in shared
-//                memory, which is torch.argmin's comparator.
-//                A point whose best distance is <= D_near is CERTIFIED: every cylinder that could beat or tie it has
-//                lb <= D_near for the point's voxel, i.e. sits in the near part.  The winning row is stored at the
-//                point's original row (4 bytes, L2 resident).
-//                The few points that are not certified (noise tail) then walk the FAR part of the tile, lanes across
-//                entries in ascending lb order, and stop at the first entry whose lb exceeds their incumbent.
+//     evaluate:  every lane owns a (voxel, <= 2 points) slot of the sorted cloud and walks the NEAR part of its own
+//                voxel's tile (lanes of one voxel read the same 32-byte records: one L1 request), computing for every
+//                entry a ~30-instruction closed-form distance ESTIMATE in cylinder-local coordinates.  When the best
+//                estimate beats the runner-up by more than twice the rounding allowance, no entry is numerically
+//                delicate, and the best is within D_near, the winner is decided without a single reference-order
+//                evaluation (the epilogue computes the winner's distance and offset in reference order anyway).
+//                The other points (~8 %: near-ties, interior points, the noise tail) take the exact path: lanes across
+//                the tile's entries in ascending lower-bound order, capsule cull against the estimate, survivors
+//                queued and evaluated 32 at a time with the reference arithmetic, 64-bit (distance, row) keys —
+//                torch.argmin's comparator.  A point whose exact best distance is <= D_near is CERTIFIED: every
+//                cylinder that could beat or tie it has lb <= D_near for the point's voxel, i.e. sits in the near
+//                part; the noise tail walks on into the FAR part and stops at the first entry whose lb exceeds the
+//                incumbent.  The winning row is stored at the point's original row (4 bytes, L2 resident).
 //     ring:      a handful of points still uncertified at D_max (noise tail): ball query over the neighbouring voxels'
 //                tiles, one CTA per point (latency-optimised).
 //     tree:      MANY such points (clutter far from every cylinder) and points outside the grid descend the
@@ -165,7 +166,7 @@ constexpr int SORT_WARPS = 8;
 __global__ void __launch_bounds__(SORT_WARPS * 32)
 tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ cell_cnt, uint32_t ncodes,
                  const unsigned long long *__restrict__ tile_keys, const float4 *__restrict__ recA,
-                 const float4 *__restrict__ recB, float near_reach, float4 *__restrict__ tileA, float4 *__restrict__ tileB,
+                 const float4 *__restrict__ recB, float near_reach, float4 *__restrict__ tileAB,
                  int32_t *__restrict__ tileI, float *__restrict__ tileLB, uint32_t *__restrict__ cell_near,
                  unsigned int *__restrict__ n_with_tiles) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
@@ -201,8 +202,8 @@ tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__rest
                 const unsigned long long key = buf[i];
                 const uint32_t c = static_cast<uint32_t>(key);
                 const float lb = __uint_as_float(static_cast<uint32_t>(key >> 32));
-                tileA[off + i] = recA[c];
-                tileB[off + i] = recB[c];
+                tileAB[2 * static_cast<size_t>(off + i)] = recA[c];
+                tileAB[2 * static_cast<size_t>(off + i) + 1] = recB[c];
                 tileI[off + i] = static_cast<int32_t>(c);
                 tileLB[off + i] = lb;
                 near += lb <= near_reach ? 1u : 0u;
@@ -211,8 +212,8 @@ tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__rest
         } else {
             for (uint32_t i = lane; i < n; i += 32) {
                 const uint32_t c = static_cast<uint32_t>(tile_keys[off + i]);
-                tileA[off + i] = recA[c];
-                tileB[off + i] = recB[c];
+                tileAB[2 * static_cast<size_t>(off + i)] = recA[c];
+                tileAB[2 * static_cast<size_t>(off + i) + 1] = recB[c];
                 tileI[off + i] = static_cast<int32_t>(c);
                 tileLB[off + i] = 0.f;
             }
@@ -220,7 +221,6 @@ tile_sort_kernel(const uint32_t *__restrict__ cell_start, const uint32_t *__rest
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) near += __shfl_xor_sync(0xffffffffu, near, o);
-        if (n - near > 0xFFFFFFu) near = n;          // the far length must fit the 24 bits of a work item
         if (lane == 0) cell_near[code] = near;
     }
     if (lane == 0 && with_tiles) atomicAdd(n_with_tiles, with_tiles);
@@ -242,7 +242,7 @@ __global__ void align4_kernel(const uint32_t *__restrict__ cnt, uint32_t *__rest
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;     // 4096 voxels per block
-constexpr int PTS_PER_ITEM = 64;
+constexpr int PTS_PER_LANE = 2;           // points of ONE voxel a lane of the tile kernel owns (a "lane slot")
 constexpr int CELL_PAD = 4;               // uint2 slots per voxel cell: one 32-byte sector each, so that neighbouring voxels'
                                           // atomics do not queue up on a shared sector
 
@@ -285,7 +285,7 @@ __device__ __forceinline__ Tri block_exclusive_scan(Tri v, Tri *total) {
 }
 
 __device__ __forceinline__ Tri tri_of_count(uint32_t cnt) {
-    return Tri{cnt, cnt ? 1u : 0u, (cnt + PTS_PER_ITEM - 1) / PTS_PER_ITEM};
+    return Tri{cnt, cnt ? 1u : 0u, (cnt + PTS_PER_LANE - 1) / PTS_PER_LANE};
 }
 
 // phase A: per-block totals
@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(Tri *__restri
     if (threadIdx.x == 0 && st) {
         st->points_binned = carry.a;
         st->voxels_occupied = carry.b;
-        st->work_items = carry.c;
+        st->work_items = carry.b;
+        st->lane_slots = carry.c;
     }
 }
 
@@ -343,8 +344,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(Tri *__restri
 // In mode 1 `count` and `start` are the SAME array of {count, start} cells (stride 2): a thread reads the counts of its
 // own cells, then rewrites them as {0, start} — the low word becomes the scatter pass's cursor, so that ONE 64-bit
 // atomicAdd returns both the run start and the slot inside the run.
-// mode 1 (points): start[code] = first sorted point of the voxel, and the voxel's work items
-// {tile offset, near length, first point, point count <= 64 | far length << 8} are emitted in voxel-id order.
+// mode 1 (points): start[code] = first sorted point of the voxel; every occupied voxel becomes one item
+// {tile offset, near length, first point, point count} + {far length, first lane slot}, in voxel-id order, and every
+// group of 32 lane slots learns which item its first slot belongs to (warp_item).
 template <int NSUB>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *count, int stride, uint32_t ncodes,
                                                                   const Tri *__restrict__ block_sums, int mode,
@@ -352,7 +354,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
                                                                   const uint32_t *__restrict__ tile_start,
                                                                   const uint32_t *__restrict__ tile_cnt,
                                                                   const uint32_t *__restrict__ tile_near,
-                                                                  uint4 *__restrict__ items) {
+                                                                  uint4 *__restrict__ items, uint2 *__restrict__ items2,
+                                                                  uint32_t *__restrict__ warp_item) {
     const int lane = threadIdx.x & 31;
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
     uint32_t cnt[SCAN_ITEMS];
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
     Tri run = tri_add(block_exclusive_scan(v, nullptr), block_sums[blockIdx.x]);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        uint32_t toff = 0, tnear = 0, far = 0, n_items = 0;
+        uint32_t q_lo = 1, q_hi = 0;                 // groups of 32 lane slots that START inside this voxel's slots
         if (base + i < ncodes) {
             if (mode == 0) {
                 start[base + i] = run.a;
@@ -380,30 +383,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
                     sub_start += c[sidx];
                 }
                 if (cnt[i]) {
-                    toff = tile_start[base + i];
-                    tnear = tile_near[base + i];
-                    far = tile_cnt[base + i] - tnear;                // < 2^24 (tile_sort_kernel)
-                    n_items = (cnt[i] + PTS_PER_ITEM - 1) / PTS_PER_ITEM;
+                    const uint32_t tnear = tile_near[base + i];
+                    items[run.b] = make_uint4(tile_start[base + i], tnear, run.a, cnt[i]);
+                    items2[run.b] = make_uint2(tile_cnt[base + i] - tnear, run.c);
+                    const uint32_t nslots = (cnt[i] + PTS_PER_LANE - 1) / PTS_PER_LANE;
+                    q_lo = (run.c + 31u) >> 5;
+                    q_hi = (run.c + nslots - 1u) >> 5;
                 }
             }
         }
-        // work items of the voxel: a few -> this thread; a crowded voxel (dense clouds: hundreds of items) -> the whole
-        // warp, so that no thread ends up writing thousands of items alone
-        if (n_items && n_items <= 4)
-            for (uint32_t t = 0; t < n_items; ++t)
-                items[run.c + t] = make_uint4(toff, tnear, run.a + t * PTS_PER_ITEM,
-                                              min(static_cast<uint32_t>(PTS_PER_ITEM), cnt[i] - t * PTS_PER_ITEM) | (far << 8));
-        uint32_t crowded = __ballot_sync(0xffffffffu, n_items > 4);
+        // a few groups -> this thread; a crowded voxel (dense clouds: thousands of points) -> the whole warp
+        if (q_lo <= q_hi && q_hi - q_lo < 4u)
+            for (uint32_t q = q_lo; q <= q_hi; ++q) warp_item[q] = run.b;
+        uint32_t crowded = __ballot_sync(0xffffffffu, q_lo <= q_hi && q_hi - q_lo >= 4u);
         while (crowded) {
             const int src = __ffs(crowded) - 1;
             crowded &= crowded - 1;
-            const uint32_t s_toff = __shfl_sync(0xffffffffu, toff, src), s_near = __shfl_sync(0xffffffffu, tnear, src),
-                           s_far = __shfl_sync(0xffffffffu, far, src), s_first = __shfl_sync(0xffffffffu, run.c, src),
-                           s_pt = __shfl_sync(0xffffffffu, run.a, src), s_cnt = __shfl_sync(0xffffffffu, cnt[i], src);
-            const uint32_t s_items = (s_cnt + PTS_PER_ITEM - 1) / PTS_PER_ITEM;
-            for (uint32_t t = lane; t < s_items; t += 32)
-                items[s_first + t] = make_uint4(s_toff, s_near, s_pt + t * PTS_PER_ITEM,
-                                                min(static_cast<uint32_t>(PTS_PER_ITEM), s_cnt - t * PTS_PER_ITEM) | (s_far << 8));
+            const uint32_t s_lo = __shfl_sync(0xffffffffu, q_lo, src), s_hi = __shfl_sync(0xffffffffu, q_hi, src),
+                           s_item = __shfl_sync(0xffffffffu, run.b, src);
+            for (uint32_t q = s_lo + lane; q <= s_hi; q += 32) warp_item[q] = s_item;
         }
         run = tri_add(run, tri_of_count(cnt[i]));
     }
@@ -411,7 +409,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 }
 
 static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mode, uint32_t *start, const uint32_t *tile_start,
-                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, DevStats *st, cudaStream_t stream, int nsub = 1) {
+                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, uint2 *items2, uint32_t *warp_item,
+                    DevStats *st, cudaStream_t stream, int nsub = 1) {
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
     Tri *bs = h->block_sums.as<Tri>();
@@ -421,7 +420,7 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
         scan_reduce_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);                                \
         scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);                                                   \
         scan_apply_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs, mode, start, tile_start, tile_cnt, \
-                                                                   tile_near, items);                                          \
+                                                                   tile_near, items, items2, warp_item);                       \
     } while (0)
     switch (nsub) {
         case 2: TM_SCAN_CASE(2); break;
@@ -436,7 +435,7 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
 
 // exclusive scan of `n` counters into start[0..n] (start[n] = total); used by the point-feature kernels (tm_knn.cu)
 int exclusive_scan_u32(tm_handle *h, const uint32_t *count, uint32_t n, uint32_t *start, cudaStream_t stream) {
-    return run_scan(h, count, n, 0, start, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    return run_scan(h, count, n, 0, start, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,7 +555,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_KCHECK(h, stream, "cyl_register_kernel (count)");
     lap("register (count)");
     align4_kernel<<<(ncodes + 255) / 256, 256, 0, stream>>>(counter, h->cyl_cell_cnt.as<uint32_t>(), rounded, ncodes);
-    int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc != TM_OK) return rc;
     uint32_t total = 0, nlong = 0;
     TM_CUDA(h, cudaMemcpyAsync(&total, h->cyl_cell_start.as<uint32_t>() + ncodes, 4, cudaMemcpyDeviceToHost, stream));
@@ -567,14 +566,12 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     h->index_entries = total;
     h->n_listed = n_regular - nlong;
     const size_t pool = static_cast<size_t>(total) + 4;
-    TM_CUDA(h, h->tileA.ensure(sizeof(float4) * pool));
-    TM_CUDA(h, h->tileB.ensure(sizeof(float4) * pool));
+    TM_CUDA(h, h->tileAB.ensure(sizeof(float4) * 2 * pool));
     TM_CUDA(h, h->tileI.ensure(sizeof(int32_t) * pool));
     TM_CUDA(h, h->tileLB.ensure(sizeof(float) * pool));
     TM_CUDA(h, h->tile_keys.ensure(sizeof(unsigned long long) * pool));
     // padding entries are copied by the bulk loads (never read): give them defined contents
-    TM_CUDA(h, cudaMemsetAsync(h->tileA.p, 0, sizeof(float4) * pool, stream));
-    TM_CUDA(h, cudaMemsetAsync(h->tileB.p, 0, sizeof(float4) * pool, stream));
+    TM_CUDA(h, cudaMemsetAsync(h->tileAB.p, 0, sizeof(float4) * 2 * pool, stream));
     TM_CUDA(h, cudaMemsetAsync(h->tileI.p, 0, sizeof(int32_t) * pool, stream));
     TM_CUDA(h, cudaMemsetAsync(h->tileLB.p, 0, sizeof(float) * pool, stream));
     TM_CUDA(h, cudaMemsetAsync(counter, 0, sizeof(uint32_t) * ncodes, stream));
@@ -589,7 +586,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     const int sort_blocks = static_cast<int>(std::min<uint32_t>((ncodes + SORT_WARPS - 1) / SORT_WARPS, static_cast<uint32_t>(h->sm_count) * 3));
     tile_sort_kernel<<<sort_blocks, SORT_WARPS * 32, sort_smem, stream>>>(
         h->cyl_cell_start.as<uint32_t>(), h->cyl_cell_cnt.as<uint32_t>(), ncodes, h->tile_keys.as<unsigned long long>(),
-        h->recA.as<float4>(), h->recB.as<float4>(), h->near, h->tileA.as<float4>(), h->tileB.as<float4>(),
+        h->recA.as<float4>(), h->recB.as<float4>(), h->near, h->tileAB.as<float4>(),
         h->tileI.as<int32_t>(), h->tileLB.as<float>(), h->cyl_cell_near.as<uint32_t>(), d_nlong);
     TM_KCHECK(h, stream, "tile_sort_kernel");
     unsigned int with_tiles = 0;
@@ -692,294 +689,400 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// evaluate: persistent warps over work items, TMA-staged tiles, cull + dense evaluation, fused record write
+// tile kernel: lane-owned (voxel, <= 2 points) slots, approximate-distance bounds over the near part of the voxel's
+// tile, reference-order evaluations only where the bounds cannot decide
 // ------------------------------------------------------------------------------------------------
+// The reference distance of a regular cylinder (unit axis, finite record) is, in exact arithmetic,
+//     inside the slab (|d| <= atol):  sqrt((rho - r)^2 + d^2)          d   = axial overshoot  t - clamp(t, 0, L)
+//     beyond a cap    (|d| >  atol):  sqrt(max(rho - r, 0)^2 + d^2)    rho = distance from the axis line
+// and what the reference computes in fp32 differs from it by a few ulp of the largest coordinate in play, which `slack`
+// (= S below) bounds with a wide margin.  bound_pair() evaluates that closed form in coordinates relative to the
+// cylinder's start (a few ulp of the LOCAL magnitudes, far inside S) and reports
+//     D      squared distance estimate (+inf for an unreliable entry)
+//     unrel  the estimate cannot be trusted to S: the point is inside the radius where the two forms differ and
+//            |d| is within S of atol (for variant A this is every interior point of the slab: the reference's d is
+//            rounding noise of the size of its atol = 1e-6), or the point is within S of the axis line (rho -> 0: the
+//            reference divides by rho; variant A yields NaN there, which wins the argmin).
+// With b = argmin D, m1 = D_b, m2 = min_{j != b} D_j over the reliable entries, no unreliable entry and
+// sqrt(m2) - sqrt(m1) > 2 S:
+//     ref_b <= sqrt(m1) + S < sqrt(m2) - S <= ref_j   for every j != b,
+// so b is the reference's argmin among the tile's near entries with no tie, and it is the argmin over ALL cylinders when
+// (sqrt(m1) + S) * 1.00001 + slack <= D_near (everything outside the near part is farther than D_near from every point of
+// the voxel).  The winner's distance and offset are computed in reference order by the epilogue kernel, so such a point
+// costs no reference-order evaluation here at all.  Every other point (~8 % of a noisy surface cloud: near-ties at
+// branch junctions, interior points, the noise tail beyond D_near) takes the exact path: capsule cull against
+// thr = sqrt(m1) + S, reference-order evaluation of the survivors, 64-bit (distance, row) keys — the same machinery and
+// the same guarantees as before.
 constexpr int EV_WARPS = 8;
-constexpr int EV_CHUNK = 64;          // tile entries per stage: 64 * (16 + 16 + 4) B = 2.25 KB
-constexpr int Q_CAP = 96;             // < 32 queued pairs before a push, <= 64 pushed per entry
-
-struct __align__(128) WarpStage {
-    float4 A[2][EV_CHUNK];
-    float4 B[2][EV_CHUNK];
-    int32_t I[2][EV_CHUNK];
-    float4 P[PTS_PER_ITEM];               // the item's points {x, y, z, bits(original row)}
-    unsigned long long best[PTS_PER_ITEM];
-    uint32_t q[Q_CAP];                    // (point slot << 16) | entry position in the stage buffers
-};
+constexpr int Q_CAP = 96;             // < 32 queued pairs before a push, <= 32 pushed per step, drained in 32s
+constexpr uint32_t Q_REC = 0x80000000u;    // queue entry refers to a cylinder ROW (recA / recB) instead of a pool position
 
 struct EvalArgs {
     const uint4 *items;
-    unsigned int *cursor;
+    const uint2 *items2;
+    const uint32_t *warp_item;
+    unsigned int *cursor;         // next chunk of rounds the tile kernel hands out
     const float4 *sorted;
-    const float4 *tileA, *tileB;
+    const float4 *tileAB;
     const int32_t *tileI;
     const float4 *recA, *recB;
-    const int32_t *ids;
     const int32_t *special, *aligned, *long_list;
     uint32_t n_special, n_aligned, n_long;
     const float *tileLB;
     float atol, eps, slack, near, reach;
+    float amb;                    // S of the estimate comparison (<= slack)
+    uint4 *undecided;             // points the estimates could not decide: {sorted position, item, bits(upper bound), 0};
+    uint32_t undecided_cap;       //   near-certified ones fill the array from the front, the others from the back
     int32_t *win;                 // winning cylinder row of every certified point, at the point's original row
     int32_t *pend_idx;
     unsigned long long *pend_keys;
     DevStats *st;
 };
 
-template <bool GUARD, bool NFMA>
-__global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) {
-    extern __shared__ __align__(128) unsigned char ev_smem[];
-    WarpStage *stages = reinterpret_cast<WarpStage *>(ev_smem);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ev_smem + sizeof(WarpStage) * EV_WARPS);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t lt = (1u << lane) - 1u;
-    WarpStage &ws = stages[warp];
-    uint64_t *bar = bars + 2 * warp;
-    if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-    const uint32_t n_items = a.st->work_items;
-    uint32_t fill = 0, use = 0;          // chunks issued / consumed by this warp
+struct Track {                    // per point: smallest and second smallest squared estimate, entry of the smallest
+    float m1, m2;                 // m2 < 0: some entry was unreliable
+    uint32_t bj;
+};
 
-    auto issue_chunk = [&](uint32_t pool_off, uint32_t cnt) {
-        if (lane == 0) {
-            const int s = fill & 1;
-            const uint32_t cnt4 = (cnt + 3u) & ~3u;
-            mbar_expect_tx(&bar[s], cnt4 * 36u);
-            bulk_g2s(&ws.A[s][0], a.tileA + pool_off, cnt4 * 16u, &bar[s]);
-            bulk_g2s(&ws.B[s][0], a.tileB + pool_off, cnt4 * 16u, &bar[s]);
-            bulk_g2s(&ws.I[s][0], a.tileI + pool_off, cnt4 * 4u, &bar[s]);
-        }
-        ++fill;
-    };
+// WIDE: atol > 2 S, i.e. there is a band |d| < atol - S in which the reference's perp decision is certainly `true`
+// (variant B, atol = 1e-3); otherwise (variant A) every |d| <= atol + S is undecided.
+template <bool WIDE>
+__device__ __forceinline__ void bound_pair(float px, float py, float pz, const float4 A, const float4 B, float band_lo,
+                                           float band_hi, float S, float rho2_min, uint32_t j, Track &tr) {
+    const float vx = px - A.x, vy = py - A.y, vz = pz - A.z;
+    const float t = fmaf(vz, B.z, fmaf(vy, B.y, vx * B.x));
+    const float tc = fminf(fmaxf(t, 0.f), A.w);
+    const float d = t - tc;
+    const float rx = fmaf(-t, B.x, vx), ry = fmaf(-t, B.y, vy), rz = fmaf(-t, B.z, vz);     // rejection from the axis LINE
+    const float rho2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+    const float rho = rho2 * mufu_rsq(fmaxf(rho2, 1e-30f));
+    const float a = rho - B.w;
+    const float ad = fabsf(d);
+    const bool beyond = ad > band_hi;                       // certainly not perp
+    const bool undecided = WIDE ? (!beyond && ad >= band_lo) : !beyond;
+    const float asel = beyond ? fmaxf(a, 0.f) : a;
+    const bool unrel = (undecided && a < S) || rho2 < rho2_min;
+    // an unreliable entry gives no upper bound either (variant B divides by max(rho, 1e-8): with rho below the guard the
+    // foot point collapses towards the axis and the distance grows to sqrt(d^2 + r^2)): it only forces the exact path
+    const float D = unrel ? __int_as_float(0x7f800000) : fmaf(asel, asel, d * d);
+    tr.m2 = fminf(tr.m2, fmaxf(tr.m1, D));
+    tr.bj = D < tr.m1 ? j : tr.bj;
+    tr.m1 = fminf(tr.m1, D);
+    tr.m2 = unrel ? -1.f : tr.m2;
+}
+
+// warp-aggregated append of the lanes with `want` to a list that grows up (dir = +1, from `origin`) or down (dir = -1);
+// returns the lane's slot
+__device__ __forceinline__ uint32_t warp_append(bool want, unsigned int *counter, uint32_t lane, uint32_t lt) {
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    uint32_t base = 0;
+    if (m) {
+        if (lane == 0) base = atomicAdd(counter, static_cast<unsigned int>(__popc(m)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+    }
+    return base + __popc(m & lt);
+}
+
+constexpr uint32_t EV_CHUNK_ROUNDS = 4;        // consecutive rounds (groups of 32 lane slots) a warp takes per cursor fetch
+
+struct __align__(16) StageScratch {           // undecided points wait here until 32 of a kind can be written with one atomic
+    uint4 front[64];
+    uint4 back[64];
+};
+
+template <bool WIDE>
+__global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) {
+    __shared__ StageScratch stage[EV_WARPS];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    StageScratch &sg = stage[threadIdx.x >> 5];
+    const uint32_t n_items = a.st->work_items, total_slots = a.st->lane_slots;
+    const uint32_t n_wslots = (total_slots + 31u) >> 5;
+    const uint32_t n_chunks = (n_wslots + EV_CHUNK_ROUNDS - 1u) / EV_CHUNK_ROUNDS;
+    const uint32_t n_sorted = static_cast<uint32_t>(a.st->points_binned);
+    const float S = a.amb;
+    const float band_hi = a.atol + S, band_lo = a.atol - S, rho2_min = S * S;
+    const bool lists = (a.n_special | a.n_long | a.n_aligned) != 0u;     // warp-uniform: every point takes the exact kernel
+    const float INF = __int_as_float(0x7f800000);
+
     auto fetch = [&]() {
         uint32_t v = 0;
         if (lane == 0) v = atomicAdd(a.cursor, 1u);
         return __shfl_sync(0xffffffffu, v, 0);
     };
-
-    uint32_t cur = fetch();
-    uint4 it = cur < n_items ? a.items[cur] : make_uint4(0, 0, 0, 0);
-    bool cur_ready = false;
-    unsigned long long pairs = 0, culls = 0;
-    unsigned int nfar = 0;
-    while (cur < n_items) {
-        const uint32_t nxt = fetch();
-        const uint4 itn = nxt < n_items ? a.items[nxt] : make_uint4(0, 0, 0, 0);
-        bool nxt_ready = false;
-        const uint32_t pool_off = it.x, tcount = it.y, pbeg = it.z, pcnt = it.w & 0xffu, far_cnt = it.w >> 8;
-        if (tcount > 0 && !cur_ready) issue_chunk(pool_off, min(static_cast<uint32_t>(EV_CHUNK), tcount));
-        const bool v0 = static_cast<uint32_t>(lane) < pcnt, v1 = static_cast<uint32_t>(lane) + 32u < pcnt;
-        const float4 P0 = a.sorted[pbeg + min(static_cast<uint32_t>(lane), pcnt - 1)];
-        const float4 P1 = a.sorted[pbeg + min(static_cast<uint32_t>(lane) + 32u, pcnt - 1)];
-        ws.P[lane] = P0;
-        ws.P[lane + 32] = P1;
-        ws.best[lane] = KEY_NONE;
-        ws.best[lane + 32] = KEY_NONE;
+    uint32_t nf = 0, nb = 0;                  // staged undecided points (warp-uniform)
+    auto flush = [&](uint4 *buf, uint32_t &cnt, unsigned int *counter, bool down) {
         __syncwarp();
-        float thr0 = __int_as_float(0x7f800000), thr1 = thr0;
-        uint32_t qn = 0;
+        const uint32_t n = min(cnt, 32u);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n) a.undecided[down ? a.undecided_cap - 1u - (base + lane) : base + lane] = buf[lane];
+        __syncwarp();
+        const uint4 rest = buf[32 + lane];
+        __syncwarp();
+        if (32u + lane < cnt) buf[lane] = rest;
+        cnt -= n;
+        __syncwarp();
+    };
+    auto stage_append = [&](bool want, const uint4 rec, uint4 *buf, uint32_t &cnt, unsigned int *counter, bool down) {
+        const uint32_t m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+            if (want) buf[cnt + __popc(m & lt)] = rec;
+            cnt += __popc(m);
+            if (cnt >= 32u) flush(buf, cnt, counter, down);
+        }
+    };
 
-        // evaluate up to 32 queued (point, entry) pairs with the reference arithmetic, full lanes
-        auto drain = [&]() {
-            __syncwarp();
-            const uint32_t n = min(qn, 32u);
-            if (static_cast<uint32_t>(lane) < n) {
-                const uint32_t e = ws.q[qn - n + lane];
-                const uint32_t slot = e >> 16, jj = e & 0xffffu;
-                const float4 P = ws.P[slot];
-                const float4 ca = (&ws.A[0][0])[jj], cb = (&ws.B[0][0])[jj];
-                const uint32_t ci = static_cast<uint32_t>((&ws.I[0][0])[jj]);
-                const float d = eval_pair<GUARD, NFMA, false>(P.x, P.y, P.z, ca, cb, a.atol, a.eps, nullptr);
-                atomicMin(&ws.best[slot], make_key(d, ci));
+    unsigned int bounds = 0;
+    uint32_t chunk = fetch();
+    while (chunk < n_chunks) {
+        const uint32_t next_chunk = fetch();
+        const uint32_t r_end = min((chunk + 1u) * EV_CHUNK_ROUNDS, n_wslots);
+        for (uint32_t cur = chunk * EV_CHUNK_ROUNDS; cur < r_end; ++cur) {
+            // ---- which voxel run does this lane's slot belong to?  The warp's 32 slots span at most 32 consecutive items.
+            const uint32_t it0 = a.warp_item[cur];
+            const uint32_t mine = it0 + lane < n_items ? a.items2[it0 + lane].y : 0xFFFFFFFFu;
+            const uint32_t s = (cur << 5) + lane;
+            const bool valid = s < total_slots;
+            uint32_t lo = 0, hi = 32;
+#pragma unroll
+            for (int step = 0; step < 5; ++step) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(0xffffffffu, mine, mid);
+                if (v <= s) lo = mid; else hi = mid;
             }
-            qn -= n;
-            pairs += n;
-            __syncwarp();
-            thr0 = thr_of(ws.best[lane], a.slack);
-            thr1 = thr_of(ws.best[lane + 32], a.slack);
-        };
+            const uint32_t slot_start = __shfl_sync(0xffffffffu, mine, lo);
+            const uint32_t item = it0 + lo;
+            const uint4 it = valid ? a.items[item] : make_uint4(0, 0, 0, 0);
+            const uint32_t tile_off = it.x, near_cnt = it.y;
+            const uint32_t k = valid ? s - slot_start : 0u;
+            const uint32_t p0 = it.z + PTS_PER_LANE * k;
+            const bool v0 = valid, v1 = valid && PTS_PER_LANE * k + 1u < it.w;
+            const float4 *tile = a.tileAB + 2 * static_cast<size_t>(tile_off);
+            // the lane's tile is read entry by entry below: ask for all of its 128-byte lines now (lanes of one voxel ask
+            // for the same lines), so that the loop finds them in L1 instead of paying the L2 latency once per entry
+            for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
+            const float4 P0 = v0 ? a.sorted[p0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 P1 = v1 ? a.sorted[p0 + 1] : P0;
+            // the following rounds of the chunk continue where this one ends, in the sorted cloud and in the item arrays:
+            // their lines can be asked for now (no address depends on anything still in flight) — points two rounds ahead,
+            // item records one round ahead, and the tiles of the next few items as soon as their records are here (below)
+            uint2 ahead = make_uint2(0u, 0u);
+            if (cur + 1u < r_end) {
+                const uint32_t p_end = __reduce_max_sync(0xffffffffu, valid ? p0 + 2u : 0u);
+                const uint32_t i_end = __reduce_max_sync(0xffffffffu, valid ? item : 0u);
+                const uint32_t p_from = p_end + (cur == chunk * EV_CHUNK_ROUNDS ? 0u : 64u);       // first round of a chunk: both
+                if (lane < 16) { if (p_from + 8u * lane < n_sorted) prefetch_l1(a.sorted + p_from + 8u * lane); }
+                else if (lane < 20) { if (i_end + 8u * (lane - 16u) < n_items) prefetch_l1(a.items + i_end + 8u * (lane - 16u)); }
+                else if (lane < 22) { if (i_end + 16u * (lane - 20u) < n_items) prefetch_l1(a.items2 + i_end + 16u * (lane - 20u)); }
+                else if (lane < 28) { if (i_end + (lane - 21u) < n_items) { const uint4 nx = a.items[i_end + (lane - 21u)]; ahead = make_uint2(nx.x, nx.y); } }
+            }
 
-        if (tcount > 0) {
-            const uint32_t nchunks = (tcount + EV_CHUNK - 1) / EV_CHUNK;
-            const bool two = pcnt > 32u;
-            for (uint32_t ch = 0; ch < nchunks; ++ch) {
-                // keep one copy in flight: the next chunk of this tile, else the next item's first chunk
-                if (ch + 1 < nchunks) {
-                    issue_chunk(pool_off + (ch + 1) * EV_CHUNK, min(static_cast<uint32_t>(EV_CHUNK), tcount - (ch + 1) * EV_CHUNK));
-                } else if (nxt < n_items && itn.y > 0) {
-                    issue_chunk(itn.x, min(static_cast<uint32_t>(EV_CHUNK), itn.y));
-                    nxt_ready = true;
+            // ---- estimates over the near part of the lane's own tile, entries double-buffered in registers
+            Track t0{INF, INF, 0u}, t1{INF, INF, 0u};
+            const uint32_t max_near = __reduce_max_sync(0xffffffffu, near_cnt);
+            float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
+            if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
+            for (uint32_t j = 0; j < max_near; j += 2) {
+                if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
+                if (j < near_cnt) {
+                    bound_pair<WIDE>(P0.x, P0.y, P0.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t0);
+                    bound_pair<WIDE>(P1.x, P1.y, P1.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t1);
                 }
-                const int s = use & 1;
-                mbar_wait(&bar[s], (use >> 1) & 1);
-                ++use;
-                const uint32_t cnt = min(static_cast<uint32_t>(EV_CHUNK), tcount - ch * EV_CHUNK);
-                if (two) {
-                    for (uint32_t j = 0; j < cnt; ++j) {
-                        const float4 ca = ws.A[s][j];
-                        const float4 cb = ws.B[s][j];
-                        const bool p0 = cull_pass(P0.x, P0.y, P0.z, ca, cb, thr0);           // lanes >= 32 carry duplicates:
-                        const bool p1 = v1 && cull_pass(P1.x, P1.y, P1.z, ca, cb, thr1);     // all of P0 is valid when two
-                        const uint32_t m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
-                        if (m0 | m1) {
-                            const uint32_t e = static_cast<uint32_t>(s * EV_CHUNK) + j;
-                            const uint32_t n0 = __popc(m0);
-                            if (p0) ws.q[qn + __popc(m0 & lt)] = (static_cast<uint32_t>(lane) << 16) | e;
-                            if (p1) ws.q[qn + n0 + __popc(m1 & lt)] = (static_cast<uint32_t>(lane + 32) << 16) | e;
-                            qn += n0 + __popc(m1);
-                            while (qn >= 32u) drain();
-                        }
+                if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
+                if (j + 1u < near_cnt) {
+                    bound_pair<WIDE>(P0.x, P0.y, P0.z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, t0);
+                    bound_pair<WIDE>(P1.x, P1.y, P1.z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, t1);
+                }
+            }
+            bounds += near_cnt * ((v0 ? 1u : 0u) + (v1 ? 1u : 0u));
+            for (uint32_t e = 0; e < min(ahead.y, 12u); e += 4) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(ahead.x + e));
+
+            // ---- decided by the estimates alone?  (d1 = NaN without a reliable entry: every comparison below fails)
+            const float d10 = t0.m1 * mufu_rsq(fmaxf(t0.m1, 1e-30f)), d11 = t1.m1 * mufu_rsq(fmaxf(t1.m1, 1e-30f));
+            const float up0 = fmaf(d10 + S, 1.00001f, a.slack), up1 = fmaf(d11 + S, 1.00001f, a.slack);   // >= thr of the exact winner
+            const bool cert0 = up0 <= a.near, cert1 = up1 <= a.near;
+            const float w0 = d10 + 2.f * S, w1 = d11 + 2.f * S;
+            const bool fast0 = v0 && !lists && cert0 && t0.m2 > w0 * w0;          // m2 = -1 (unreliable entry) fails
+            const bool fast1 = v1 && !lists && cert1 && t1.m2 > w1 * w1;
+            if (fast0) a.win[__float_as_int(P0.w)] = a.tileI[tile_off + t0.bj];
+            if (fast1) a.win[__float_as_int(P1.w)] = a.tileI[tile_off + t1.bj];
+
+            if (__any_sync(0xffffffffu, (v0 && !fast0) || (v1 && !fast1))) {
+                // voxels without any tile entry (clutter far from every cylinder) and no list to run: straight to the pending list
+                const bool empty = !lists && valid && near_cnt == 0u && a.items2[item].x == 0u;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const bool todo = kk ? (v1 && !fast1) : (v0 && !fast0);
+                    const bool cert = kk ? cert1 : cert0;
+                    const uint4 rec = make_uint4(p0 + kk, item, __float_as_uint(kk ? up1 : up0), 0u);
+                    stage_append(todo && !empty && cert, rec, sg.front, nf, &a.st->undecided_near, false);
+                    stage_append(todo && !empty && !cert, rec, sg.back, nb, &a.st->undecided_far, true);
+                    const bool pend = todo && empty;
+                    const uint32_t sp = warp_append(pend, &a.st->pending, lane, lt);
+                    if (pend) {
+                        a.pend_idx[sp] = __float_as_int(kk ? P1.w : P0.w);
+                        a.pend_keys[sp] = KEY_NONE;
                     }
+                }
+            }
+        }
+        chunk = next_chunk;
+    }
+    while (nf) flush(sg.front, nf, &a.st->undecided_near, false);
+    while (nb) flush(sg.back, nb, &a.st->undecided_far, true);
+    unsigned long long all_bounds = bounds;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) all_bounds += __shfl_xor_sync(0xffffffffu, all_bounds, o);
+    if (lane == 0 && all_bounds) atomicAdd(&a.st->bound_tests, all_bounds);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact kernel: the points the estimates left undecided, 32 per warp, each lane walking its own point's tile in
+// ascending lower-bound order: capsule cull against the point's upper bound, survivors queued per warp and evaluated 32
+// at a time with the reference arithmetic (full lanes), 64-bit (distance, row) keys in shared memory.
+// Near-certified points (front of the list) stop at the end of the near part; the others (back of the list: the noise
+// tail) walk on through the FAR part and stop at the first entry whose lower bound exceeds their incumbent, so the two
+// kinds never share a warp and the walks of a warp have similar lengths.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) ExactScratch {
+    float4 P[32];
+    unsigned long long best[32];
+    uint2 q[Q_CAP];                           // {pool position (or row | Q_REC), lane of the point}
+};
+
+template <bool GUARD, bool NFMA>
+__global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
+    __shared__ ExactScratch scratch[EV_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    ExactScratch &ws = scratch[warp];
+    const uint32_t n_front = a.st->undecided_near, n_back = a.st->undecided_far;
+    const uint32_t w_front = (n_front + 31u) >> 5, w_all = w_front + ((n_back + 31u) >> 5);
+    const float INF = __int_as_float(0x7f800000);
+    unsigned int pairs = 0, culls = 0, nfar = 0;
+    uint32_t qn = 0;
+
+    auto drain = [&]() {
+        __syncwarp();
+        const uint32_t n = min(qn, 32u);
+        if (lane < n) {
+            const uint2 e = ws.q[qn - n + lane];
+            const float4 P = ws.P[e.y];
+            float4 ca, cb;
+            uint32_t ci;
+            if (e.x & Q_REC) { ci = e.x & ~Q_REC; ca = a.recA[ci]; cb = a.recB[ci]; }
+            else { ca = a.tileAB[2 * static_cast<size_t>(e.x)]; cb = a.tileAB[2 * static_cast<size_t>(e.x) + 1]; ci = static_cast<uint32_t>(a.tileI[e.x]); }
+            const float d = eval_pair<GUARD, NFMA, false>(P.x, P.y, P.z, ca, cb, a.atol, a.eps, nullptr);
+            atomicMin(&ws.best[e.y], make_key(d, ci));
+        }
+        qn -= n;
+        pairs += n;
+        __syncwarp();
+    };
+    auto push = [&](bool hit, uint32_t pos) {
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            if (hit) ws.q[qn + __popc(m & lt)] = make_uint2(pos, lane);
+            qn += __popc(m);
+        }
+        return m != 0u;
+    };
+
+    for (uint32_t w = blockIdx.x * EV_WARPS + warp; w < w_all; w += gridDim.x * EV_WARPS) {
+        const bool is_front = w < w_front;
+        const uint32_t idx = (is_front ? w : w - w_front) * 32u + lane;
+        const bool valid = idx < (is_front ? n_front : n_back);
+        const uint4 rec = valid ? a.undecided[is_front ? idx : a.undecided_cap - 1u - idx] : make_uint4(0, 0, 0, 0);
+        const float4 P = valid ? a.sorted[rec.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint4 it = valid ? a.items[rec.y] : make_uint4(0, 0, 0, 0);
+        const uint32_t far_cnt = valid ? a.items2[rec.y].x : 0u;
+        const uint32_t off = it.x;
+        const uint32_t total = valid ? (is_front ? it.y : it.y + far_cnt) : 0u;
+        float thr = __uint_as_float(rec.z);            // NaN without a reliable estimate: nothing is culled
+        // the walk below reads the lane's tile entry by entry: ask for the first lines now, the rest as the walk advances
+        if (total) {
+            prefetch_l1(a.tileLB + off);
+            for (uint32_t e = 0; e < min(total, 16u); e += 4) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + e));
+        }
+        ws.P[lane] = P;
+        ws.best[lane] = KEY_NONE;
+        __syncwarp();
+        bool cut = false;
+        uint32_t live = __ballot_sync(0xffffffffu, total > 0u);
+        for (uint32_t j = 0; live; ++j) {
+            bool hit = false;
+            if (!cut && j < total) {
+                if ((j & 3u) == 0u && j + 16u < total) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + j + 16u));
+                if ((j & 31u) == 0u && j + 32u < total) prefetch_l1(a.tileLB + off + j + 32u);
+                const float lb = a.tileLB[off + j];
+                if (lb > thr) {
+                    cut = true;                           // everything from here on is farther than the incumbent
                 } else {
-                    for (uint32_t j = 0; j < cnt; ++j) {
-                        const float4 ca = ws.A[s][j];
-                        const float4 cb = ws.B[s][j];
-                        const bool p0 = v0 && cull_pass(P0.x, P0.y, P0.z, ca, cb, thr0);
-                        const uint32_t m0 = __ballot_sync(0xffffffffu, p0);
-                        if (m0) {
-                            if (p0) ws.q[qn + __popc(m0 & lt)] = (static_cast<uint32_t>(lane) << 16) | (static_cast<uint32_t>(s * EV_CHUNK) + j);
-                            qn += __popc(m0);
-                            while (qn >= 32u) drain();
-                        }
-                    }
+                    const float4 ca = a.tileAB[2 * static_cast<size_t>(off + j)], cb = a.tileAB[2 * static_cast<size_t>(off + j) + 1];
+                    hit = cull_pass(P.x, P.y, P.z, ca, cb, thr);
+                    ++culls;
                 }
-                while (qn) drain();      // the queue refers to this stage's buffers: empty it before they are re-armed
-                __syncwarp();
             }
-            culls += static_cast<unsigned long long>(pcnt) * tcount;
+            push(hit, off + j);
+            if (qn >= 32u) {
+                drain();
+                thr = fminf(thr, thr_of(ws.best[lane], a.slack));     // fminf ignores a NaN operand
+            }
+            live = __ballot_sync(0xffffffffu, !cut && j + 1u < total);
         }
-        unsigned long long k0 = ws.best[lane], k1 = ws.best[lane + 32];
-
-        // cylinders spanning too many voxels to be listed: cull test against every point
-        for (uint32_t e = 0; e < a.n_long; ++e) {
-            const uint32_t ci = static_cast<uint32_t>(a.long_list[e]);
-            const float4 ca = a.recA[ci], cb = a.recB[ci];
-            if (cull_pass(P0.x, P0.y, P0.z, ca, cb, thr_of(k0, a.slack))) {
-                const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(P0.x, P0.y, P0.z, ca, cb, a.atol, a.eps, nullptr), ci);
-                k0 = k < k0 ? k : k0;
-            }
-            if (cull_pass(P1.x, P1.y, P1.z, ca, cb, thr_of(k1, a.slack))) {
-                const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(P1.x, P1.y, P1.z, ca, cb, a.atol, a.eps, nullptr), ci);
-                k1 = k < k1 ? k : k1;
-            }
-        }
-        // cylinders that cannot be bounded (non-finite / non-unit axis): evaluated for every point
+        // cylinders that cannot be bounded (non-finite / non-unit axis): evaluated for every point; cylinders spanning too
+        // many voxels to be listed: cull test; variant A: points exactly on the axis line of an axis-parallel cylinder get
+        // NaN from it (and NaN wins)
         for (uint32_t e = 0; e < a.n_special; ++e) {
-            const uint32_t ci = static_cast<uint32_t>(a.special[e]);
-            const float4 ca = a.recA[ci], cb = a.recB[ci];
-            const unsigned long long q0 = make_key(eval_pair<GUARD, NFMA, false>(P0.x, P0.y, P0.z, ca, cb, a.atol, a.eps, nullptr), ci);
-            const unsigned long long q1 = make_key(eval_pair<GUARD, NFMA, false>(P1.x, P1.y, P1.z, ca, cb, a.atol, a.eps, nullptr), ci);
-            k0 = q0 < k0 ? q0 : k0;
-            k1 = q1 < k1 ? q1 : k1;
+            push(valid, static_cast<uint32_t>(a.special[e]) | Q_REC);
+            while (qn >= 32u) drain();
         }
-        // variant A: points exactly on the axis line of an axis-parallel cylinder get NaN from it (and NaN wins)
+        if (a.n_long) {
+            while (qn) drain();
+            thr = fminf(thr, thr_of(ws.best[lane], a.slack));
+            for (uint32_t e = 0; e < a.n_long; ++e) {
+                const uint32_t ci = static_cast<uint32_t>(a.long_list[e]);
+                const bool hit = valid && cull_pass(P.x, P.y, P.z, a.recA[ci], a.recB[ci], thr);
+                culls += valid ? 1u : 0u;
+                push(hit, ci | Q_REC);
+                while (qn >= 32u) drain();
+            }
+        }
         if (!GUARD) {
             for (uint32_t e = 0; e < a.n_aligned; ++e) {
                 const uint32_t ci = static_cast<uint32_t>(a.aligned[e]);
-                const float4 ca = a.recA[ci], cb = a.recB[ci];
-                if (on_axis_line(P0.x, P0.y, P0.z, ca, cb)) {
-                    const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(P0.x, P0.y, P0.z, ca, cb, a.atol, a.eps, nullptr), ci);
-                    k0 = k < k0 ? k : k0;
-                }
-                if (on_axis_line(P1.x, P1.y, P1.z, ca, cb)) {
-                    const unsigned long long k = make_key(eval_pair<GUARD, NFMA, false>(P1.x, P1.y, P1.z, ca, cb, a.atol, a.eps, nullptr), ci);
-                    k1 = k < k1 ? k : k1;
-                }
+                push(valid && on_axis_line(P.x, P.y, P.z, a.recA[ci], a.recB[ci]), ci | Q_REC);
+                while (qn >= 32u) drain();
             }
         }
-        pairs += static_cast<unsigned long long>(pcnt) * a.n_special;
-        culls += static_cast<unsigned long long>(pcnt) * a.n_long;
-
-        // ---- points the near part cannot certify (noise tail): the FAR part of the tile, one point at a time with the
-        //      lanes across entries.  Entries are sorted by lb(V, c) <= dist(p, capsule(c)); the first entry whose lb
-        //      exceeds the incumbent ends the search (everything behind it, and every cylinder outside the tile, is
-        //      farther than the incumbent); an exhausted tile certifies incumbents <= D_max.
-        bool far0 = false, far1 = false;
-        {
-            const bool need0 = v0 && static_cast<uint32_t>(k0 >> 32) != 0u && !(thr_of(k0, a.slack) <= a.near);
-            const bool need1 = v1 && static_cast<uint32_t>(k1 >> 32) != 0u && !(thr_of(k1, a.slack) <= a.near);
-            const uint32_t nm0 = __ballot_sync(0xffffffffu, need0), nm1 = __ballot_sync(0xffffffffu, need1);
-            if (nm0 | nm1) {
-                const uint32_t far_off = pool_off + tcount;
-#pragma unroll 1
-                for (int k = 0; k < 2; ++k) {
-                    uint32_t mask = k ? nm1 : nm0;
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float4 Pk = k ? P1 : P0;
-                        const float px = __shfl_sync(0xffffffffu, Pk.x, src), py = __shfl_sync(0xffffffffu, Pk.y, src),
-                                    pz = __shfl_sync(0xffffffffu, Pk.z, src);
-                        unsigned long long key = __shfl_sync(0xffffffffu, k ? k1 : k0, src);
-                        float thr = thr_of(key, a.slack);                  // NaN while there is no incumbent: nothing is skipped
-                        bool cut = false;
-                        for (uint32_t base = 0; base < far_cnt; base += 32) {
-                            const uint32_t j = base + lane;
-                            const float lb = j < far_cnt ? a.tileLB[far_off + j] : __int_as_float(0x7f800000);
-                            if (__shfl_sync(0xffffffffu, lb, 0) > thr) { cut = true; break; }
-                            unsigned long long lk = KEY_NONE;
-                            const bool test = j < far_cnt && !(lb > thr);
-                            bool hit = false;
-                            if (test) {
-                                const float4 ca = a.tileA[far_off + j], cb = a.tileB[far_off + j];
-                                hit = cull_pass(px, py, pz, ca, cb, thr);
-                                if (hit) lk = make_key(eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr),
-                                                       static_cast<uint32_t>(a.tileI[far_off + j]));
-                            }
-                            culls += __popc(__ballot_sync(0xffffffffu, test));
-                            pairs += __popc(__ballot_sync(0xffffffffu, hit));
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                const unsigned long long other = __shfl_xor_sync(0xffffffffu, lk, o);
-                                lk = other < lk ? other : lk;
-                            }
-                            if (lk < key) { key = lk; thr = thr_of(key, a.slack); }
-                        }
-                        const bool ok = static_cast<uint32_t>(key >> 32) == 0u || cut || thr <= a.reach;
-                        if (lane == src) {
-                            if (k) { k1 = key; far1 = ok; } else { k0 = key; far0 = ok; }
-                        }
-                    }
-                }
-                nfar += __popc(__ballot_sync(0xffffffffu, far0)) + __popc(__ballot_sync(0xffffffffu, far1));
-            }
+        while (qn) drain();
+        const unsigned long long key = ws.best[lane];
+        thr = fminf(thr, thr_of(key, a.slack));
+        // NaN incumbent (hi word 0) is final: NaN beats everything.  Near-certified: the exact distance is inside D_near.
+        // Otherwise: an entry beyond the incumbent ended the walk, or the whole tile was searched and the incumbent is
+        // inside D_max — everything else is farther.  KEY_NONE is never certified.
+        const bool nan_key = static_cast<uint32_t>(key >> 32) == 0u;
+        const bool near_ok = thr_of(key, a.slack) <= a.near;
+        const bool far_ok = !is_front && key != KEY_NONE && (cut || thr <= a.reach);
+        const bool done = valid && (nan_key || near_ok || far_ok);
+        if (done) a.win[__float_as_int(P.w)] = static_cast<int32_t>(key_index(key));
+        nfar += __popc(__ballot_sync(0xffffffffu, done && !nan_key && !near_ok));
+        const bool pend = valid && !done;
+        const uint32_t sp = warp_append(pend, &a.st->pending, lane, lt);
+        if (pend) {
+            a.pend_idx[sp] = __float_as_int(P.w);
+            a.pend_keys[sp] = key;
         }
-
-        // ---- certified points: the winning row goes to the point's ORIGINAL row (a 4-byte scatter into an array that
-        //      stays L2 resident); the streaming epilogue kernel turns rows into labels + offsets with coalesced
-        //      reads and writes.  The rest join the pending list (tree search) with their incumbent ----
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const bool valid = k ? v1 : v0;
-            const float4 P = k ? P1 : P0;
-            const unsigned long long key = k ? k1 : k0;
-            // NaN incumbent (hi word 0) is final: NaN beats everything.  KEY_NONE gives thr = NaN: not certified.
-            const bool done = valid && (static_cast<uint32_t>(key >> 32) == 0u || thr_of(key, a.slack) <= a.near || (k ? far1 : far0));
-            const bool pend = valid && !done;
-            if (done) a.win[__float_as_int(P.w)] = static_cast<int32_t>(key_index(key));
-            const uint32_t pm = __ballot_sync(0xffffffffu, pend);
-            if (pm) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(&a.st->pending, static_cast<unsigned int>(__popc(pm)));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pend) {
-                    const unsigned int s = base + __popc(pm & lt);
-                    a.pend_idx[s] = __float_as_int(P.w);
-                    a.pend_keys[s] = key;
-                }
-            }
-        }
-        __syncwarp();                    // ws.P / ws.best are rewritten by the next item
-        cur = nxt;
-        it = itn;
-        cur_ready = nxt_ready;
+        __syncwarp();                    // ws.P / ws.best are rewritten by the next round
     }
-    if (lane == 0 && (pairs | culls)) {
-        atomicAdd(&a.st->pairs_grid, pairs);
-        atomicAdd(&a.st->cull_tests, culls);
+    unsigned long long all_culls = culls;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) all_culls += __shfl_xor_sync(0xffffffffu, all_culls, o);
+    if (lane == 0 && (pairs | all_culls)) {
+        atomicAdd(&a.st->pairs_grid, static_cast<unsigned long long>(pairs));
+        atomicAdd(&a.st->cull_tests, all_culls);
         if (nfar) atomicAdd(&a.st->far_certified, nfar);
     }
 }
@@ -1000,7 +1103,7 @@ struct RingArgs {
     unsigned long long *pend_keys;
     uint8_t *pend_done;            // 1 = this slot is final (the tree search skips it)
     const uint32_t *tile_start, *tile_cnt;
-    const float4 *tileA, *tileB;
+    const float4 *tileAB;
     const int32_t *tileI;
     float atol, eps;
     DevStats *st;
@@ -1117,7 +1220,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
                         if (s_beg[mid] <= e) lo = mid; else hi = mid;
                     }
                     const uint32_t pos = s_off[lo] + (e - s_beg[lo]);
-                    const float4 ca = a.tileA[pos], cb = a.tileB[pos];
+                    const float4 ca = a.tileAB[2 * static_cast<size_t>(pos)], cb = a.tileAB[2 * static_cast<size_t>(pos) + 1];
                     ++culls;
                     if (cull_pass(px, py, pz, ca, cb, lthr)) {
                         const float d = eval_pair<GUARD, NFMA, false>(px, py, pz, ca, cb, a.atol, a.eps, nullptr);
@@ -1174,7 +1277,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
 
     // scratch
     const size_t max_occ = std::min<size_t>(n, ncodes);
-    const size_t max_items = n / PTS_PER_ITEM + max_occ + 1;
+    const size_t max_wslots = (n / PTS_PER_LANE + max_occ) / 32 + 2;
     // dense clouds (hundreds of points per voxel) queue their atomics on the voxels' counters: split each counter into
     // 2 / 4 / 8 sub-cells.  The density is judged by the voxels that have a tile at all (known per table).
     int nsub = 1;
@@ -1185,7 +1288,10 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     }
     TM_CUDA(h, h->cells.ensure(sizeof(uint2) * CELL_PAD * nsub * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
-    TM_CUDA(h, h->items.ensure(sizeof(uint4) * max_items));
+    TM_CUDA(h, h->items.ensure(sizeof(uint4) * (max_occ + 1)));
+    TM_CUDA(h, h->items2.ensure(sizeof(uint2) * (max_occ + 1)));
+    TM_CUDA(h, h->warp_item.ensure(sizeof(uint32_t) * max_wslots));
+    TM_CUDA(h, h->undecided.ensure(sizeof(uint4) * n));
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
     TM_CUDA(h, h->brute_slots.ensure(sizeof(uint32_t) * n));
     TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * n));
@@ -1205,7 +1311,8 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     TM_KCHECK(h, st, "bin_count_kernel");
     mark(h, 1, st);
     int rc = run_scan(h, h->cells.as<uint32_t>(), ncodes, 1, h->cells.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
-                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), dst, st, nsub);
+                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), h->items2.as<uint2>(),
+                      h->warp_item.as<uint32_t>(), dst, st, nsub);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
     mark(h, 2, st);
@@ -1215,9 +1322,11 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     mark(h, 3, st);
     EvalArgs ev;
     ev.items = h->items.as<uint4>();
+    ev.items2 = h->items2.as<uint2>();
+    ev.warp_item = h->warp_item.as<uint32_t>();
     ev.cursor = cursor;
     ev.sorted = h->sorted_pts.as<float4>();
-    ev.tileA = h->tileA.as<float4>(); ev.tileB = h->tileB.as<float4>(); ev.tileI = h->tileI.as<int32_t>();
+    ev.tileAB = h->tileAB.as<float4>(); ev.tileI = h->tileI.as<int32_t>();
     ev.recA = h->recA.as<float4>(); ev.recB = h->recB.as<float4>();
     ev.special = h->special.as<int32_t>();
     ev.aligned = h->aligned.as<int32_t>();
@@ -1226,24 +1335,27 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.atol = a.prm.perp_atol; ev.eps = a.prm.norm_eps;
     ev.tileLB = h->tileLB.as<float>();
     ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
+    // allowance of the estimate-vs-reference comparison: the same rounding slack by default (TM_AMB_FACTOR scales it down
+    // for experiments; never above the slack)
+    ev.amb = slack;
+    if (const char *env = getenv("TM_AMB_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v > 0.f && v <= 1.f) ev.amb = slack * v; }
     int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();       // the caller's index array doubles as the scatter target
     ev.win = win;
+    ev.undecided = h->undecided.as<uint4>();
+    ev.undecided_cap = static_cast<uint32_t>(n);
     ev.pend_idx = h->pend_idx.as<int32_t>();
     ev.pend_keys = h->keys.as<unsigned long long>();
     ev.st = dst;
-    const size_t ev_smem = sizeof(WarpStage) * EV_WARPS + sizeof(uint64_t) * 2 * EV_WARPS;
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
+    const bool wide = a.prm.perp_atol > 2.f * ev.amb;
+    if (guard) ev.n_aligned = 0;              // variant B never yields NaN on an axis line
     const int ev_blocks = h->sm_count * 4;
-#define TM_EVAL_CASE(G, F)                                                                                         \
-    do {                                                                                                           \
-        TM_CUDA(h, cudaFuncSetAttribute(evaluate_kernel<G, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                        static_cast<int>(ev_smem)));                                               \
-        evaluate_kernel<G, F><<<ev_blocks, EV_WARPS * 32, ev_smem, st>>>(ev);                                      \
-    } while (0)
-    if (guard) { if (nfma) TM_EVAL_CASE(true, true); else TM_EVAL_CASE(true, false); }
-    else       { if (nfma) TM_EVAL_CASE(false, true); else TM_EVAL_CASE(false, false); }
-#undef TM_EVAL_CASE
+    if (wide) evaluate_kernel<true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev);
+    else evaluate_kernel<false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev);
     TM_KCHECK(h, st, "evaluate_kernel");
+    if (guard) { if (nfma) exact_kernel<true, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
+    else       { if (nfma) exact_kernel<false, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
+    TM_KCHECK(h, st, "exact_kernel");
 
     // still uncertified at D_max (beyond the far part of their own tile): a handful of points -> ring search, one CTA per
     // point; many (clutter), or outside the grid -> per-point descent of the bounding-volume hierarchy
@@ -1254,7 +1366,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     rg.pend_keys = h->keys.as<unsigned long long>();
     rg.pend_done = h->pend_done.as<uint8_t>();
     rg.tile_start = h->cyl_cell_start.as<uint32_t>(); rg.tile_cnt = h->cyl_cell_cnt.as<uint32_t>();
-    rg.tileA = h->tileA.as<float4>(); rg.tileB = h->tileB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
+    rg.tileAB = h->tileAB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
     rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
     rg.st = dst;
     const int rg_blocks = h->sm_count * (2048 / (RING_WARPS * 32));

@@ -58,6 +58,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ uint32_t lane_id() {
     uint32_t l;
     asm("mov.u32 %0, %%laneid;" : "=r"(l));

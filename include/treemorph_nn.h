@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TM_ABI_VERSION 5
+#define TM_ABI_VERSION 6
 
 /* status codes */
 #define TM_OK               0
@@ -93,12 +93,17 @@ typedef struct tm_stats {
     uint64_t points_brute;      /* points answered by the exhaustive kernel (non-finite points, brute mode)  */
     uint64_t index_entries;     /* (voxel, cylinder) entries of the static voxel index                       */
     uint32_t voxels_occupied;   /* voxels holding at least one point                                         */
-    uint32_t work_items;        /* (voxel, <=64-point slice) items processed by the tile kernel              */
+    uint32_t work_items;        /* occupied voxels (one tile descriptor each) processed by the tile kernel   */
     uint32_t mode_used;         /* TM_MODE_BRUTE or TM_MODE_GRID                                             */
     float    cell_size;         /* voxel edge actually used                                                  */
     float    reach;             /* D_max: a tile lists every cylinder within D_max of its voxel              */
     float    near_reach;        /* D_near: radius covered by the near part of a tile (<= reach)              */
     uint32_t grid_dim[3];       /* voxel grid extent                                                         */
+    uint32_t launches;          /* kernels the call launched                                                 */
+    uint64_t bound_tests;       /* closed-form distance estimates (point, tile entry) of the tile kernel     */
+    uint64_t points_slow;       /* points the tile kernel settled with reference-order evaluations           */
+    uint32_t lane_ops_per_bound;/* FP32 lane-operations of one estimate (the F of its roofline share)        */
+    uint32_t reserved;
 } tm_stats;
 
 int tm_version(void);                                   /* returns TM_ABI_VERSION                     */

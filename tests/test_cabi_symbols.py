@@ -37,7 +37,7 @@ def test_abi_version_and_struct_layout():
     lib = binding.load()
     assert lib.tm_version() == binding.ABI_VERSION
     assert ctypes.sizeof(binding.TmParams) == 32
-    assert ctypes.sizeof(binding.TmStats) == 104
+    assert ctypes.sizeof(binding.TmStats) == 128
     assert lib.tm_status_string(binding.TM_ERR_NO_CYLINDERS).decode().startswith("argmin()")
 
 
