@@ -330,11 +330,12 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
                      const float4 *__restrict__ recAB, const int32_t *__restrict__ ids,
                      float atol, float eps, int move_to_mantle, int32_t *__restrict__ out_index, int32_t *__restrict__ out_id,
                      float *__restrict__ out_dist, float *__restrict__ out_offset, float *__restrict__ out_radius,
-                     float4 *__restrict__ out_packed) {
+                     float4 *__restrict__ out_packed, const uint32_t *__restrict__ rows, const unsigned int *__restrict__ d_count) {
     // two rows per thread and iteration: both rows' loads (point, winning row, then the dependent record gathers) are in
     // flight together, which is what hides the L2 latency of the gathers
     constexpr int R = 2;
     const int64_t span = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    if (rows) n = *d_count;                       // list mode: the rows to finish are rows[0 .. *d_count)
     for (int64_t row0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; row0 < n; row0 += R * span) {
         int64_t row[R];
         bool ok[R];
@@ -344,7 +345,8 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
         for (int k = 0; k < R; ++k) {
             row[k] = row0 + k * span;
             ok[k] = row[k] < n;
-            const int64_t r = ok[k] ? row[k] : row0;
+            if (rows) row[k] = rows[ok[k] ? row[k] : row0];
+            const int64_t r = (ok[k] || rows) ? row[k] : row0;
             j[k] = static_cast<uint32_t>(win[r]);
             const float *p = pts + r * row_stride;
             px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
@@ -371,14 +373,14 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
     }
 }
 
-int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win) {
+int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win, const uint32_t *rows, const unsigned int *d_count) {
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
     const int grid = static_cast<int>(std::min<int64_t>((a.n + 511) / 512, static_cast<int64_t>(h->sm_count) * 16));
 #define TM_FINR_CASE(G, F)                                                                                          \
     finalize_rows_kernel<G, F><<<grid, 256, 0, a.stream>>>(a.pts, a.n, a.row_stride, win, h->recAB.as<float4>(),     \
                                                            h->ids.as<int32_t>(), a.prm.perp_atol,                       \
                                                            a.prm.norm_eps, a.prm.move_to_mantle, a.out_index, a.out_id, \
-                                                           a.out_dist, a.out_offset, a.out_radius, a.out_packed)
+                                                           a.out_dist, a.out_offset, a.out_radius, a.out_packed, rows, d_count)
     if (guard) { if (nfma) TM_FINR_CASE(true, true); else TM_FINR_CASE(true, false); }
     else       { if (nfma) TM_FINR_CASE(false, true); else TM_FINR_CASE(false, false); }
 #undef TM_FINR_CASE

@@ -84,6 +84,7 @@ struct DevStats {
     unsigned int undecided_near;     // points the estimates left undecided but certified inside D_near (front of the list)
     unsigned int undecided_far;      // points the estimates could not certify inside D_near (back of the list)
     unsigned long long bound_tests;  // approximate-distance bounds computed by the tile kernel
+    unsigned int late_rows;          // direct path: rows whose outputs are written by the list epilogue
 };
 
 // FP32 lane-operations of one closed-form distance estimate of the tile kernel (tm_grid.cu: bound_pair), counted the way
@@ -144,6 +145,8 @@ struct tm_handle {
     tmn::DevBuf items2;              // uint2 per occupied voxel {far length, first lane slot}
     tmn::DevBuf warp_item;           // uint32 per group of 32 lane slots: the item its first slot belongs to
     tmn::DevBuf undecided;           // uint4 per point the estimates left undecided (exact kernel's work list)
+    tmn::DevBuf late_rows;           // uint32: rows the direct kernel did not finish itself
+    tmn::DevBuf tile_desc;           // uint4 per voxel code {tile offset, near length, tile length, 0} (static, per table)
     tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)
     tmn::DevBuf brute_slots;         // uint32 pending slots that need the exhaustive kernel
     tmn::DevBuf pend_done;           // uint8 per pending slot: 1 = final after the ring search
@@ -239,7 +242,8 @@ int label_brute(tm_handle *h, const LabelArgs &a);
 // slots listed in h->brute_slots, then the winning row of EVERY pending slot goes to win[original row]
 int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win, float maxabs);
 // streaming winner-only epilogue over all rows: win[row] -> index / id / distance / offset / radius
-int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win);
+// rows == nullptr: every row 0..n-1; else the *d_count rows listed in `rows`
+int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win, const uint32_t *rows, const unsigned int *d_count);
 // tm_small.cu
 constexpr int SMALL_MAX_M = 3072;     // cylinders per call of the small-table kernel (2 x 16 B of shared memory each)
 struct SmallArgs {

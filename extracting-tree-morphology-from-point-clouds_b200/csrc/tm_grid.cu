@@ -236,6 +236,13 @@ __global__ void align4_kernel(const uint32_t *__restrict__ cnt, uint32_t *__rest
     rounded[i] = (c + 3u) & ~3u;
 }
 
+// per voxel code {tile offset, near length, tile length, 0}: what the direct path gathers once per point
+__global__ void tile_desc_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ near,
+                                 uint4 *__restrict__ desc, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) desc[i] = make_uint4(start[i], near[i], cnt[i], 0u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // generic 3-channel exclusive scan over the voxel arrays (points, occupied flags, work items)
 // ------------------------------------------------------------------------------------------------
@@ -593,6 +600,10 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_CUDA(h, cudaMemcpyAsync(&with_tiles, d_nlong, sizeof(with_tiles), cudaMemcpyDeviceToHost, stream));
     TM_CUDA(h, cudaStreamSynchronize(stream));
     h->voxels_with_tiles = with_tiles;
+    TM_CUDA(h, h->tile_desc.ensure(sizeof(uint4) * static_cast<size_t>(ncodes)));
+    tile_desc_kernel<<<(ncodes + 255) / 256, 256, 0, stream>>>(h->cyl_cell_start.as<uint32_t>(), h->cyl_cell_cnt.as<uint32_t>(),
+                                                             h->cyl_cell_near.as<uint32_t>(), h->tile_desc.as<uint4>(), ncodes);
+    TM_KCHECK(h, stream, "tile_desc_kernel");
     lap("tile sort");
     // (tile_keys is build-time scratch, kept for the next table: cudaFree + cudaMalloc cost more than the build's kernels)
     rc = build_bvh(h, stream, static_cast<int>(n_regular), lo, hi);
@@ -737,6 +748,10 @@ struct EvalArgs {
     int32_t *pend_idx;
     unsigned long long *pend_keys;
     DevStats *st;
+    // direct path: the records of `undecided` are {row, voxel code, bits(upper bound), 0}
+    const float *pts;
+    int64_t row_stride;
+    const uint4 *tile_desc;       // per voxel code {tile offset, near length, tile length, 0}
 };
 
 struct Track {                    // per point: smallest and second smallest squared estimate, entry of the smallest
@@ -783,6 +798,7 @@ __device__ __forceinline__ uint32_t warp_append(bool want, unsigned int *counter
     return base + __popc(m & lt);
 }
 
+constexpr int EV_BLOCKS_PER_SM = PTS_PER_LANE > 2 ? 3 : 4;
 constexpr uint32_t EV_CHUNK_ROUNDS = 4;        // consecutive rounds (groups of 32 lane slots) a warp takes per cursor fetch
 
 struct __align__(16) StageScratch {           // undecided points wait here until 32 of a kind can be written with one atomic
@@ -791,7 +807,7 @@ struct __align__(16) StageScratch {           // undecided points wait here unti
 };
 
 template <bool WIDE>
-__global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kernel(EvalArgs a) {
     __shared__ StageScratch stage[EV_WARPS];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -858,71 +874,85 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) evaluate_kernel(EvalArgs a) 
             const uint32_t tile_off = it.x, near_cnt = it.y;
             const uint32_t k = valid ? s - slot_start : 0u;
             const uint32_t p0 = it.z + PTS_PER_LANE * k;
-            const bool v0 = valid, v1 = valid && PTS_PER_LANE * k + 1u < it.w;
+            bool pv[PTS_PER_LANE];
+#pragma unroll
+            for (int q = 0; q < PTS_PER_LANE; ++q) pv[q] = valid && PTS_PER_LANE * k + q < it.w;
             const float4 *tile = a.tileAB + 2 * static_cast<size_t>(tile_off);
             // the lane's tile is read entry by entry below: ask for all of its 128-byte lines now (lanes of one voxel ask
             // for the same lines), so that the loop finds them in L1 instead of paying the L2 latency once per entry
             for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
-            const float4 P0 = v0 ? a.sorted[p0] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 P1 = v1 ? a.sorted[p0 + 1] : P0;
+            float4 P[PTS_PER_LANE];
+            P[0] = pv[0] ? a.sorted[p0] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 1; q < PTS_PER_LANE; ++q) P[q] = pv[q] ? a.sorted[p0 + q] : P[0];
             // the following rounds of the chunk continue where this one ends, in the sorted cloud and in the item arrays:
             // their lines can be asked for now (no address depends on anything still in flight) — points two rounds ahead,
             // item records one round ahead, and the tiles of the next few items as soon as their records are here (below)
             uint2 ahead = make_uint2(0u, 0u);
             if (cur + 1u < r_end) {
-                const uint32_t p_end = __reduce_max_sync(0xffffffffu, valid ? p0 + 2u : 0u);
+                constexpr uint32_t RP = 32 * PTS_PER_LANE;                  // points per round, at most
+                const uint32_t p_end = __reduce_max_sync(0xffffffffu, valid ? p0 + PTS_PER_LANE : 0u);
                 const uint32_t i_end = __reduce_max_sync(0xffffffffu, valid ? item : 0u);
-                const uint32_t p_from = p_end + (cur == chunk * EV_CHUNK_ROUNDS ? 0u : 64u);       // first round of a chunk: both
-                if (lane < 16) { if (p_from + 8u * lane < n_sorted) prefetch_l1(a.sorted + p_from + 8u * lane); }
-                else if (lane < 20) { if (i_end + 8u * (lane - 16u) < n_items) prefetch_l1(a.items + i_end + 8u * (lane - 16u)); }
-                else if (lane < 22) { if (i_end + 16u * (lane - 20u) < n_items) prefetch_l1(a.items2 + i_end + 16u * (lane - 20u)); }
-                else if (lane < 28) { if (i_end + (lane - 21u) < n_items) { const uint4 nx = a.items[i_end + (lane - 21u)]; ahead = make_uint2(nx.x, nx.y); } }
+                const uint32_t p_from = p_end + (cur == chunk * EV_CHUNK_ROUNDS ? 0u : RP);       // first round of a chunk: both
+                if (lane < RP / 4) { if (p_from + 8u * lane < n_sorted) prefetch_l1(a.sorted + p_from + 8u * lane); }
+                if (lane >= 16 && lane < 20) { if (i_end + 8u * (lane - 16u) < n_items) prefetch_l1(a.items + i_end + 8u * (lane - 16u)); }
+                else if (lane >= 20 && lane < 22) { if (i_end + 16u * (lane - 20u) < n_items) prefetch_l1(a.items2 + i_end + 16u * (lane - 20u)); }
+                else if (lane >= 22 && lane < 28) { if (i_end + (lane - 21u) < n_items) { const uint4 nx = a.items[i_end + (lane - 21u)]; ahead = make_uint2(nx.x, nx.y); } }
             }
 
             // ---- estimates over the near part of the lane's own tile, entries double-buffered in registers
-            Track t0{INF, INF, 0u}, t1{INF, INF, 0u};
+            Track tr[PTS_PER_LANE];
+#pragma unroll
+            for (int q = 0; q < PTS_PER_LANE; ++q) tr[q] = Track{INF, INF, 0u};
             const uint32_t max_near = __reduce_max_sync(0xffffffffu, near_cnt);
             float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
             if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
             for (uint32_t j = 0; j < max_near; j += 2) {
                 if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
                 if (j < near_cnt) {
-                    bound_pair<WIDE>(P0.x, P0.y, P0.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t0);
-                    bound_pair<WIDE>(P1.x, P1.y, P1.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t1);
+#pragma unroll
+                    for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A0, B0, band_lo, band_hi, S, rho2_min, j, tr[q]);
                 }
                 if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
                 if (j + 1u < near_cnt) {
-                    bound_pair<WIDE>(P0.x, P0.y, P0.z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, t0);
-                    bound_pair<WIDE>(P1.x, P1.y, P1.z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, t1);
+#pragma unroll
+                    for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, tr[q]);
                 }
             }
-            bounds += near_cnt * ((v0 ? 1u : 0u) + (v1 ? 1u : 0u));
+            uint32_t npts = 0;
+#pragma unroll
+            for (int q = 0; q < PTS_PER_LANE; ++q) npts += pv[q] ? 1u : 0u;
+            bounds += near_cnt * npts;
             for (uint32_t e = 0; e < min(ahead.y, 12u); e += 4) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(ahead.x + e));
 
             // ---- decided by the estimates alone?  (d1 = NaN without a reliable entry: every comparison below fails)
-            const float d10 = t0.m1 * mufu_rsq(fmaxf(t0.m1, 1e-30f)), d11 = t1.m1 * mufu_rsq(fmaxf(t1.m1, 1e-30f));
-            const float up0 = fmaf(d10 + S, 1.00001f, a.slack), up1 = fmaf(d11 + S, 1.00001f, a.slack);   // >= thr of the exact winner
-            const bool cert0 = up0 <= a.near, cert1 = up1 <= a.near;
-            const float w0 = d10 + 2.f * S, w1 = d11 + 2.f * S;
-            const bool fast0 = v0 && !lists && cert0 && t0.m2 > w0 * w0;          // m2 = -1 (unreliable entry) fails
-            const bool fast1 = v1 && !lists && cert1 && t1.m2 > w1 * w1;
-            if (fast0) a.win[__float_as_int(P0.w)] = a.tileI[tile_off + t0.bj];
-            if (fast1) a.win[__float_as_int(P1.w)] = a.tileI[tile_off + t1.bj];
+            float up[PTS_PER_LANE];
+            bool cert[PTS_PER_LANE], todo[PTS_PER_LANE];
+            bool any_todo = false;
+#pragma unroll
+            for (int q = 0; q < PTS_PER_LANE; ++q) {
+                const float d1 = tr[q].m1 * mufu_rsq(fmaxf(tr[q].m1, 1e-30f));
+                up[q] = fmaf(d1 + S, 1.00001f, a.slack);                     // >= thr of the exact winner
+                cert[q] = up[q] <= a.near;
+                const float w = d1 + 2.f * S;
+                const bool fast = pv[q] && !lists && cert[q] && tr[q].m2 > w * w;      // m2 = -1 (unreliable entry) fails
+                if (fast) a.win[__float_as_int(P[q].w)] = a.tileI[tile_off + tr[q].bj];
+                todo[q] = pv[q] && !fast;
+                any_todo = any_todo || todo[q];
+            }
 
-            if (__any_sync(0xffffffffu, (v0 && !fast0) || (v1 && !fast1))) {
+            if (__any_sync(0xffffffffu, any_todo)) {
                 // voxels without any tile entry (clutter far from every cylinder) and no list to run: straight to the pending list
                 const bool empty = !lists && valid && near_cnt == 0u && a.items2[item].x == 0u;
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const bool todo = kk ? (v1 && !fast1) : (v0 && !fast0);
-                    const bool cert = kk ? cert1 : cert0;
-                    const uint4 rec = make_uint4(p0 + kk, item, __float_as_uint(kk ? up1 : up0), 0u);
-                    stage_append(todo && !empty && cert, rec, sg.front, nf, &a.st->undecided_near, false);
-                    stage_append(todo && !empty && !cert, rec, sg.back, nb, &a.st->undecided_far, true);
-                    const bool pend = todo && empty;
+                for (int q = 0; q < PTS_PER_LANE; ++q) {
+                    const uint4 rec = make_uint4(p0 + q, item, __float_as_uint(up[q]), 0u);
+                    stage_append(todo[q] && !empty && cert[q], rec, sg.front, nf, &a.st->undecided_near, false);
+                    stage_append(todo[q] && !empty && !cert[q], rec, sg.back, nb, &a.st->undecided_far, true);
+                    const bool pend = todo[q] && empty;
                     const uint32_t sp = warp_append(pend, &a.st->pending, lane, lt);
                     if (pend) {
-                        a.pend_idx[sp] = __float_as_int(kk ? P1.w : P0.w);
+                        a.pend_idx[sp] = __float_as_int(P[q].w);
                         a.pend_keys[sp] = KEY_NONE;
                     }
                 }
@@ -952,7 +982,7 @@ struct __align__(16) ExactScratch {
     uint2 q[Q_CAP];                           // {pool position (or row | Q_REC), lane of the point}
 };
 
-template <bool GUARD, bool NFMA>
+template <bool GUARD, bool NFMA, bool DIRECT>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
     __shared__ ExactScratch scratch[EV_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -995,11 +1025,22 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
         const uint32_t idx = (is_front ? w : w - w_front) * 32u + lane;
         const bool valid = idx < (is_front ? n_front : n_back);
         const uint4 rec = valid ? a.undecided[is_front ? idx : a.undecided_cap - 1u - idx] : make_uint4(0, 0, 0, 0);
-        const float4 P = valid ? a.sorted[rec.x] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint4 it = valid ? a.items[rec.y] : make_uint4(0, 0, 0, 0);
-        const uint32_t far_cnt = valid ? a.items2[rec.y].x : 0u;
-        const uint32_t off = it.x;
-        const uint32_t total = valid ? (is_front ? it.y : it.y + far_cnt) : 0u;
+        float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t off = 0, total = 0;
+        if (valid) {
+            if (DIRECT) {
+                const float *p = a.pts + static_cast<int64_t>(rec.x) * a.row_stride;
+                P = make_float4(p[0], p[1], p[2], __uint_as_float(rec.x));
+                const uint4 d = a.tile_desc[rec.y];
+                off = d.x;
+                total = is_front ? d.y : d.z;
+            } else {
+                P = a.sorted[rec.x];
+                const uint4 it = a.items[rec.y];
+                off = it.x;
+                total = is_front ? it.y : it.y + a.items2[rec.y].x;
+            }
+        }
         float thr = __uint_as_float(rec.z);            // NaN without a reliable estimate: nothing is culled
         // the walk below reads the lane's tile entry by entry: ask for the first lines now, the rest as the walk advances
         if (total) {
@@ -1084,6 +1125,164 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
         atomicAdd(&a.st->pairs_grid, static_cast<unsigned long long>(pairs));
         atomicAdd(&a.st->cull_tests, all_culls);
         if (nfar) atomicAdd(&a.st->far_certified, nfar);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct path: no sort at all.  One thread per point in INPUT order: voxel id -> the voxel's tile descriptor (one 16-byte
+// gather) -> estimates over the near part of the tile (32-byte gathers that hit L2; lanes of a warp sit in different
+// voxels unless the cloud is spatially coherent) -> when the estimates decide, the winner is evaluated in reference
+// order on the spot and label + offset are written in input order (coalesced): no counting sort, no scan over the voxels,
+// no separate epilogue, no per-call cost that does not scale with the number of points.  Undecided points go to the
+// exact kernel, stragglers to the ring / tree search as before, and a short epilogue finishes exactly those rows.
+// To keep the lanes of a warp in step, the 256 points of a block are first ordered by the length of their tile's near
+// part (counting sort in shared memory): a warp then loops over similar lengths instead of the longest of 32 random ones.
+// ------------------------------------------------------------------------------------------------
+constexpr int DIRECT_THREADS = 256;
+constexpr uint32_t DIRECT_BINS = 64;          // near lengths 0..62 get their own bin, longer ones share the last
+
+struct DirectArgs {
+    const float *pts;
+    int64_t n, row_stride;
+    const uint4 *tile_desc;       // per voxel code {tile offset, near length, tile length, 0}
+    EvalArgs ev;
+    const float4 *recAB;
+    const int32_t *ids;
+    int move_to_mantle;
+    int32_t *out_index, *out_id;
+    float *out_dist, *out_offset, *out_radius;
+    float4 *out_packed;
+    uint32_t *late_rows;          // rows that did not get their outputs here (finished by finalize_list_kernel)
+    uint32_t *brute_slots;
+};
+
+template <bool GUARD, bool NFMA, bool WIDE>
+__global__ void __launch_bounds__(DIRECT_THREADS, 6) direct_kernel(DirectArgs a, GridDev g) {
+    __shared__ uint32_t s_hist[DIRECT_BINS];
+    __shared__ uint32_t s_perm[DIRECT_THREADS];
+    __shared__ float4 s_pt[DIRECT_THREADS];       // {x, y, z, bits(near length)}
+    __shared__ uint2 s_tile[DIRECT_THREADS];      // {tile offset | code}
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const EvalArgs &e = a.ev;
+    const float S = e.amb;
+    const float band_hi = e.atol + S, band_lo = e.atol - S, rho2_min = S * S;
+    const bool lists = (e.n_special | e.n_long | e.n_aligned) != 0u;
+    const float INF = __int_as_float(0x7f800000);
+    unsigned int bounds = 0, evals = 0;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * DIRECT_THREADS; base < a.n; base += static_cast<int64_t>(gridDim.x) * DIRECT_THREADS) {
+        // ---- load, bin, order by near length
+        if (tid < DIRECT_BINS) s_hist[tid] = 0;
+        __syncthreads();
+        const int64_t i = base + tid;
+        uint32_t code = NO_CELL, bin = DIRECT_BINS - 1u, rank = 0;
+        uint4 desc = make_uint4(0, 0, 0, 0);
+        float x = 0.f, y = 0.f, z = 0.f;
+        const bool have = i < a.n;
+        if (have) {
+            const float *p = a.pts + i * a.row_stride;
+            x = p[0]; y = p[1]; z = p[2];
+            code = point_code(g, x, y, z);
+            if (code != NO_CELL) desc = a.tile_desc[code];
+            bin = min(desc.y, DIRECT_BINS - 1u);
+        }
+        rank = atomicAdd(&s_hist[bin], 1u);
+        __syncthreads();
+        if (tid < 32) {                                   // exclusive scan of the 64 bins by one warp
+            const uint32_t c0 = s_hist[2 * tid], c1 = s_hist[2 * tid + 1];
+            uint32_t inc = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= static_cast<uint32_t>(o)) inc += v; }
+            s_hist[2 * tid] = inc - c0 - c1;
+            s_hist[2 * tid + 1] = inc - c1;
+        }
+        __syncthreads();
+        const uint32_t pos = s_hist[bin] + rank;
+        s_perm[pos] = tid;
+        s_pt[pos] = make_float4(x, y, z, __uint_as_float(desc.y));
+        s_tile[pos] = make_uint2(desc.x, code);
+        __syncthreads();
+        // ---- this thread now works on the point at position tid of the ordered block
+        const uint32_t src = s_perm[tid];
+        const int64_t row = base + src;
+        const bool valid = row < a.n;
+        const float4 P = s_pt[tid];
+        const uint2 tl = s_tile[tid];
+        const uint32_t near_cnt = valid ? __float_as_uint(P.w) : 0u, tile_off = tl.x, mycode = tl.y;
+        const bool inside = valid && mycode != NO_CELL;
+
+        Track t0{INF, INF, 0u};
+        const float4 *tile = e.tileAB + 2 * static_cast<size_t>(tile_off);
+        const uint32_t max_near = __reduce_max_sync(0xffffffffu, near_cnt);
+        float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
+        if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
+        for (uint32_t j = 0; j < max_near; j += 2) {
+            if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
+            if (j < near_cnt) bound_pair<WIDE>(P.x, P.y, P.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t0);
+            if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
+            if (j + 1u < near_cnt) bound_pair<WIDE>(P.x, P.y, P.z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, t0);
+        }
+        bounds += near_cnt;
+
+        const float d1 = t0.m1 * mufu_rsq(fmaxf(t0.m1, 1e-30f));
+        const float up = fmaf(d1 + S, 1.00001f, e.slack);
+        const bool cert = up <= e.near;
+        const float w = d1 + 2.f * S;
+        const bool fast = inside && !lists && cert && t0.m2 > w * w;
+        if (fast) {
+            // the winner, in reference order, and its outputs at the point's own row
+            const uint32_t pos_w = tile_off + t0.bj;
+            const uint32_t ci = static_cast<uint32_t>(e.tileI[pos_w]);
+            const float4 ca = tile[2 * t0.bj], cb = tile[2 * t0.bj + 1];
+            PairGeom gm;
+            eval_pair<GUARD, NFMA, true>(P.x, P.y, P.z, ca, cb, e.atol, e.eps, &gm);
+            float ox, oy, oz;
+            mantle_offset<NFMA>(gm, P.x, P.y, P.z, a.move_to_mantle != 0, ox, oy, oz);
+            const int32_t id = (a.out_id || a.out_packed) ? a.ids[ci] : 0;
+            e.win[row] = static_cast<int32_t>(ci);
+            if (a.out_index && a.out_index != e.win) a.out_index[row] = static_cast<int32_t>(ci);
+            if (a.out_id) a.out_id[row] = id;
+            if (a.out_dist) a.out_dist[row] = gm.dist;
+            if (a.out_offset) { a.out_offset[3 * row] = ox; a.out_offset[3 * row + 1] = oy; a.out_offset[3 * row + 2] = oz; }
+            if (a.out_radius) a.out_radius[row] = cb.w;
+            if (a.out_packed) a.out_packed[row] = make_float4(ox, oy, oz, __int_as_float(id));
+            ++evals;
+        }
+        // ---- everything else: work lists
+        const bool late = valid && !fast;
+        if (__any_sync(0xffffffffu, late)) {
+            const uint32_t sl = warp_append(late, &e.st->late_rows, lane, lt);
+            if (late) a.late_rows[sl] = static_cast<uint32_t>(row);
+            // outside the grid: straight to the tree search (non-finite coordinates: the exhaustive kernel); voxels without
+            // any tile entry and no list to run: pending without an incumbent; the rest: exact kernel
+            const uint32_t tile_total = inside ? a.tile_desc[mycode].z : 0u;
+            const bool outside = late && !inside;
+            const bool empty = late && inside && !lists && tile_total == 0u;
+            const bool pend = outside || empty;
+            const uint32_t sp = warp_append(pend, &e.st->pending, lane, lt);
+            if (pend) {
+                e.pend_idx[sp] = static_cast<int32_t>(row) | (outside ? OUTSIDE_BIT : 0);
+                e.pend_keys[sp] = KEY_NONE;
+                if (outside && !(fabsf(P.x) + fabsf(P.y) + fabsf(P.z) < 3.0e38f)) a.brute_slots[atomicAdd(&e.st->n_brute, 1u)] = sp;
+            }
+            const uint4 rec = make_uint4(static_cast<uint32_t>(row), mycode, __float_as_uint(up), 0u);
+            const bool front = late && !pend && cert, back = late && !pend && !cert;
+            const uint32_t sf = warp_append(front, &e.st->undecided_near, lane, lt);
+            if (front) e.undecided[sf] = rec;
+            const uint32_t sb = warp_append(back, &e.st->undecided_far, lane, lt);
+            if (back) e.undecided[e.undecided_cap - 1u - sb] = rec;
+        }
+        __syncthreads();                 // the shared arrays are rewritten by the next block of rows
+    }
+    unsigned long long all_bounds = bounds, all_evals = evals;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        all_bounds += __shfl_xor_sync(0xffffffffu, all_bounds, o);
+        all_evals += __shfl_xor_sync(0xffffffffu, all_evals, o);
+    }
+    if (lane == 0 && (all_bounds | all_evals)) {
+        atomicAdd(&e.st->bound_tests, all_bounds);
+        atomicAdd(&e.st->pairs_grid, all_evals);
     }
 }
 
@@ -1258,6 +1457,103 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
 // ------------------------------------------------------------------------------------------------
 // host driver
 // ------------------------------------------------------------------------------------------------
+
+// ------------------------------------------------------------------------------------------------
+// host driver of the direct path
+// ------------------------------------------------------------------------------------------------
+static bool use_direct(const tm_handle *, const LabelArgs &) {
+    static const int forced = [] { const char *e = getenv("TM_DIRECT"); return e ? atoi(e) : -1; }();
+    if (forced >= 0) return forced != 0;
+    return false;
+}
+
+static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, float slack) {
+    cudaStream_t st = a.stream;
+    const size_t n = static_cast<size_t>(a.n);
+    TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
+    TM_CUDA(h, h->brute_slots.ensure(sizeof(uint32_t) * n));
+    TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * n));
+    TM_CUDA(h, h->win.ensure(sizeof(int32_t) * n));
+    TM_CUDA(h, h->undecided.ensure(sizeof(uint4) * n));
+    TM_CUDA(h, h->late_rows.ensure(sizeof(uint32_t) * n));
+    TM_CUDA(h, h->dstats.ensure(sizeof(DevStats) + 64));
+    TM_CUDA(h, h->pend_done.ensure(n));
+    TM_CUDA(h, cudaMemsetAsync(h->pend_done.p, 0, n, st));
+    DevStats *dst = h->dstats.as<DevStats>();
+    TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
+    mark(h, 1, st); mark(h, 2, st); mark(h, 3, st);
+
+    DirectArgs d;
+    d.pts = a.pts; d.n = a.n; d.row_stride = a.row_stride;
+    d.tile_desc = h->tile_desc.as<uint4>();
+    EvalArgs &ev = d.ev;
+    ev.items = nullptr; ev.items2 = nullptr; ev.warp_item = nullptr; ev.cursor = nullptr; ev.sorted = nullptr;
+    ev.tileAB = h->tileAB.as<float4>(); ev.tileI = h->tileI.as<int32_t>();
+    ev.recA = h->recA.as<float4>(); ev.recB = h->recB.as<float4>();
+    ev.special = h->special.as<int32_t>(); ev.aligned = h->aligned.as<int32_t>(); ev.long_list = h->long_list.as<int32_t>();
+    ev.n_special = h->n_special; ev.n_aligned = h->n_aligned; ev.n_long = h->n_long;
+    ev.tileLB = h->tileLB.as<float>();
+    ev.atol = a.prm.perp_atol; ev.eps = a.prm.norm_eps;
+    ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
+    ev.amb = slack;
+    if (const char *env = getenv("TM_AMB_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v > 0.f && v <= 1.f) ev.amb = slack * v; }
+    int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();
+    ev.win = win;
+    ev.undecided = h->undecided.as<uint4>();
+    ev.undecided_cap = static_cast<uint32_t>(n);
+    ev.pend_idx = h->pend_idx.as<int32_t>();
+    ev.pend_keys = h->keys.as<unsigned long long>();
+    ev.st = dst;
+    ev.pts = a.pts; ev.row_stride = a.row_stride; ev.tile_desc = h->tile_desc.as<uint4>();
+    d.recAB = h->recAB.as<float4>();
+    d.ids = h->ids.as<int32_t>();
+    d.move_to_mantle = a.prm.move_to_mantle;
+    d.out_index = a.out_index; d.out_id = a.out_id; d.out_dist = a.out_dist; d.out_offset = a.out_offset;
+    d.out_radius = a.out_radius; d.out_packed = a.out_packed;
+    d.late_rows = h->late_rows.as<uint32_t>();
+    d.brute_slots = h->brute_slots.as<uint32_t>();
+    const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
+    const bool wide = a.prm.perp_atol > 2.f * ev.amb;
+    if (guard) ev.n_aligned = 0;
+    const int blocks = static_cast<int>(std::min<size_t>((n + DIRECT_THREADS - 1) / DIRECT_THREADS, static_cast<size_t>(h->sm_count) * 48));
+#define TM_DIRECT_CASE(G, F)                                                                                       \
+    do {                                                                                                           \
+        if (wide) direct_kernel<G, F, true><<<blocks, DIRECT_THREADS, 0, st>>>(d, g);                              \
+        else direct_kernel<G, F, false><<<blocks, DIRECT_THREADS, 0, st>>>(d, g);                                  \
+    } while (0)
+    if (guard) { if (nfma) TM_DIRECT_CASE(true, true); else TM_DIRECT_CASE(true, false); }
+    else       { if (nfma) TM_DIRECT_CASE(false, true); else TM_DIRECT_CASE(false, false); }
+#undef TM_DIRECT_CASE
+    TM_KCHECK(h, st, "direct_kernel");
+    const int ev_blocks = h->sm_count * 4;
+    if (guard) { if (nfma) exact_kernel<true, true, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
+    else       { if (nfma) exact_kernel<false, true, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<false, false, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
+    TM_KCHECK(h, st, "exact_kernel");
+
+    mark(h, 4, st);
+    RingArgs rg;
+    rg.pts = a.pts; rg.row_stride = a.row_stride;
+    rg.pend_idx = h->pend_idx.as<int32_t>();
+    rg.pend_keys = h->keys.as<unsigned long long>();
+    rg.pend_done = h->pend_done.as<uint8_t>();
+    rg.tile_start = h->cyl_cell_start.as<uint32_t>(); rg.tile_cnt = h->cyl_cell_cnt.as<uint32_t>();
+    rg.tileAB = h->tileAB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
+    rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
+    rg.st = dst;
+    const int rg_blocks = h->sm_count * (2048 / (RING_WARPS * 32));
+    if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
+    else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
+    TM_KCHECK(h, st, "ring_kernel");
+    int rc = search_bvh(h, a, dst);
+    if (rc != TM_OK) return rc;
+    mark(h, 5, st);
+    rc = finish_pending(h, a, dst, win, h->maxabs);
+    if (rc != TM_OK) return rc;
+    // outputs of the rows the direct kernel left open
+    mark(h, 7, st);
+    return finalize_rows(h, a, win, h->late_rows.as<uint32_t>(), &dst->late_rows);
+}
+
 int label_grid(tm_handle *h, const LabelArgs &a) {
     if (a.n == 0) return TM_OK;
     if (a.n > 0x7fffffffLL) return fail(h, TM_ERR_INVALID, "tm_label_points: more than 2^31-1 points per call%s%s");
@@ -1274,6 +1570,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const GridDev g = to_dev(h->grid, slack, h->reach, h->near);
     const uint32_t ncodes = h->grid.ncell_codes;
     const size_t n = static_cast<size_t>(a.n);
+    if (use_direct(h, a)) return label_direct(h, a, g, slack);
 
     // scratch
     const size_t max_occ = std::min<size_t>(n, ncodes);
@@ -1346,15 +1643,16 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.pend_idx = h->pend_idx.as<int32_t>();
     ev.pend_keys = h->keys.as<unsigned long long>();
     ev.st = dst;
+    ev.pts = a.pts; ev.row_stride = a.row_stride; ev.tile_desc = h->tile_desc.as<uint4>();
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
     const bool wide = a.prm.perp_atol > 2.f * ev.amb;
     if (guard) ev.n_aligned = 0;              // variant B never yields NaN on an axis line
     const int ev_blocks = h->sm_count * 4;
-    if (wide) evaluate_kernel<true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev);
-    else evaluate_kernel<false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev);
+    if (wide) evaluate_kernel<true><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, 0, st>>>(ev);
+    else evaluate_kernel<false><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, 0, st>>>(ev);
     TM_KCHECK(h, st, "evaluate_kernel");
-    if (guard) { if (nfma) exact_kernel<true, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
-    else       { if (nfma) exact_kernel<false, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
+    if (guard) { if (nfma) exact_kernel<true, true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
+    else       { if (nfma) exact_kernel<false, true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<false, false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
     TM_KCHECK(h, st, "exact_kernel");
 
     // still uncertified at D_max (beyond the far part of their own tile): a handful of points -> ring search, one CTA per
@@ -1383,7 +1681,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
 
     // winner-only epilogue of every row: label + offset, streaming
     mark(h, 7, st);
-    return finalize_rows(h, a, win);
+    return finalize_rows(h, a, win, nullptr, nullptr);
 }
 
 }  // namespace tmn
