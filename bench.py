@@ -455,6 +455,17 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         pinned_value = total_points * e2e_steps / float(te.item())
     pipe_pinned = eng.host_pipeline_info() if e2e_steps else pipe
+    # host memory system: the end-to-end call is bound by it (profiles/r01i_host_pipeline.md).  Bytes the host cores and the
+    # DMA engines move per point of a float64 cloud: read 24 (staging) + write 12 (page-locked float32) + DMA read 12 +
+    # DMA write 16 ({offset, id}) + read 16 + read 24 (xyz for the record) + write 56 (the (N,7) float64 record) = 160
+    host_bw = eng.host_bandwidth() if e2e_steps else None
+    host_view = None
+    if e2e_steps and e2e_value:
+        per_point = 160
+        host_view = {"host_bytes_per_point": per_point, "achieved_GBps": per_point * e2e_value / 1e9,
+                     "copy_peak_GBps": host_bw["bytes_per_s"] / 1e9, "threads": host_bw["threads"],
+                     "note": "STREAM-style copy (read + write) with the library's host workers; ranks of one node share the host"}
+        host_view["frac"] = host_view["achieved_GBps"] / host_view["copy_peak_GBps"]
 
     if rank != 0:
         if world > 1:
@@ -530,10 +541,11 @@ def main():
                    "cell_size_m": stats.get("cell_size"), "l2": "flushed between steps (256 MiB write)",
                    "parallelism": f"points sharded x{world}, cylinder table broadcast once over NCCL, no data-path collective"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_mine * 24, "d2h_bytes_per_step": n_mine * pipe["d2h_bytes_per_point"],
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_mine * 12, "d2h_bytes_per_step": n_mine * pipe["d2h_bytes_per_point"],
                 "api": "PreProcessing.LabelGenerationCuda.generate_offset_cloud_cuda_batched(float64 pageable cloud, DataFrame, device) "
-                       "-> (N,7) float64 records; table install + voxel index build inside every call",
-                "host_assembly_threads": pipe["host_threads"], "bytes_are": "per rank",
+                       "-> (N,7) float64 records; the DataFrame is read and compared with the installed table inside every call (same values: no re-install); "
+                       "host workers round the cloud to float32 into page-locked staging, 12 B/point cross PCIe",
+                "host_assembly_threads": pipe["host_threads"], "bytes_are": "per rank", "host_memory": host_view,
                 "steps": e2e_steps, "checked": e2e_ok},
         "e2e_pinned": {"value": pinned_value, "unit": UNIT, "h2d_bytes_per_step": n_mine * 12,
                        "d2h_bytes_per_step": n_mine * pipe_pinned["d2h_bytes_per_point"],

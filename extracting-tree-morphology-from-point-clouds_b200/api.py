@@ -345,6 +345,12 @@ class Engine:
         self._check(self._lib.tm_host_pipeline_info(self._h, ctypes.byref(b), ctypes.byref(t)))
         return {"d2h_bytes_per_point": int(b.value), "host_threads": int(t.value)}
 
+    def host_bandwidth(self) -> dict:
+        """Copy bandwidth (read + written bytes per second) of the host memory system with the library's worker threads."""
+        v, t = ctypes.c_double(), ctypes.c_int32()
+        self._check(self._lib.tm_measure_host_bandwidth(self._h, ctypes.byref(v), ctypes.byref(t)))
+        return {"bytes_per_s": float(v.value), "threads": int(t.value)}
+
     # -- introspection -----------------------------------------------------------------------
     def stats(self) -> dict:
         s = B.TmStats()

@@ -62,6 +62,7 @@ SIGNATURES = {
     "tm_radius_count": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_double, c_vp, c_vp]),
     "tm_noise_cloud": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_uint64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "tm_host_pipeline_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
+    "tm_measure_host_bandwidth": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i32)]),
     "tm_get_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(TmStats)]),
     "tm_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "tm_get_phase_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f32)]),

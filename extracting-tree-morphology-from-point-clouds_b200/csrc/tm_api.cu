@@ -541,6 +541,19 @@ static void assemble_rows_host(const T *cloud, int64_t row_stride, const float4 
 #endif
 }
 
+// Staging of a chunk for the H2D copy: the rows' xyz as compact float32 (n,3) in page-locked memory.  float64 clouds are
+// rounded here (RNE, what torch.tensor(points, dtype=torch.float32) does at LabelGenerationCuda.py:33), so 12 bytes per
+// point cross PCIe whatever the caller's dtype or row stride.
+template <typename T>
+static void stage_rows_f32(const T *cloud, int64_t row_stride, float *dst, int64_t r0, int64_t r1) {
+    for (int64_t r = r0; r < r1; ++r) {
+        const T *p = cloud + r * row_stride;
+        dst[3 * r + 0] = static_cast<float>(p[0]);
+        dst[3 * r + 1] = static_cast<float>(p[1]);
+        dst[3 * r + 2] = static_cast<float>(p[2]);
+    }
+}
+
 // tm_label_cloud_host, host-assembly variant: per chunk H2D -> label (packed {offset, id}) -> D2H 16 B/point, while the
 // host workers assemble earlier chunks' records.  Up to PIPE_SLOTS chunks are in flight; a chunk's buffers are reused
 // only after the chunk has been assembled (hence fully transferred).
@@ -559,20 +572,23 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     int depth = tmn::PIPE_SLOTS;
     if (const char *env = getenv("TM_HOST_DEPTH")) depth = std::max(2, std::min(tmn::PIPE_SLOTS, atoi(env)));
     const size_t esz = dtype == TM_F32 ? 4 : 8;
-    const bool in_pinned = host_is_pinned(cloud_host);
-    const size_t in_bytes = static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
+    // a page-locked compact float32 cloud is copied from where it lies; everything else (pageable memory, float64, padded
+    // rows) is staged as compact float32 by the host workers
+    const bool direct_in = host_is_pinned(cloud_host) && dtype == TM_F32 && row_stride == 3;
+    const size_t in_bytes = static_cast<size_t>(chunk) * 3 * sizeof(float);
     const size_t pk_bytes = static_cast<size_t>(chunk) * sizeof(float4);
     const size_t out_bytes = pk_bytes + static_cast<size_t>(chunk) * sizeof(float);
     // A pinned record array can also be written by the copy engine: TM_HOST_SPLIT percent of the chunks are assembled on
     // the device and DMA'd straight into the caller's rows (56 B/point over PCIe, on their own stream) while the host
-    // workers assemble the others (16 B/point + the host's stores).  See profiles/r01i_host_pipeline.md.
+    // workers assemble the others (16 B/point + the host's stores).  See profiles/r01i_host_pipeline.md.  (float32 clouds
+    // only: the device sees the float32 rounding of a float64 cloud, the records carry the caller's own values.)
     int split = 0;
-    if (const char *env = getenv("TM_HOST_SPLIT")) { if (host_is_pinned(out_records_host)) split = std::max(0, std::min(100, atoi(env))); }
+    if (const char *env = getenv("TM_HOST_SPLIT")) { if (dtype == TM_F32 && host_is_pinned(out_records_host)) split = std::max(0, std::min(100, atoi(env))); }
     auto on_device = [split](int64_t c) { return ((c + 1) * split) / 100 > (c * split) / 100; };
     for (int b = 0; b < depth; ++b) {
-        if (!in_pinned) TM_CUDA(h, h->pinned_in[b].ensure(in_bytes));
+        if (!direct_in) TM_CUDA(h, h->pinned_in[b].ensure(in_bytes));
         TM_CUDA(h, h->pinned_out[b].ensure(out_bytes));
-        TM_CUDA(h, h->chunk_in[b].ensure(in_bytes + (dtype == TM_F64 ? static_cast<size_t>(chunk) * 12 : 0)));
+        TM_CUDA(h, h->chunk_in[b].ensure(in_bytes));
         TM_CUDA(h, h->chunk_packed[b].ensure(pk_bytes));
         TM_CUDA(h, h->chunk_dist[b].ensure(static_cast<size_t>(chunk) * 4));
         if (split) {
@@ -597,32 +613,26 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     auto issue = [&](int64_t c) -> int {
         const int b = static_cast<int>(c % depth);
         const int64_t cnt = std::min(chunk, n - c * chunk);
-        const size_t bytes = static_cast<size_t>(cnt) * static_cast<size_t>(row_stride) * esz;
+        const size_t bytes = static_cast<size_t>(cnt) * 3 * sizeof(float);
         const unsigned char *csrc = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
         const double i0 = now();
-        if (!in_pinned) {
-            par_memcpy(h->pinned_in[b].p, csrc, bytes);
+        if (!direct_in) {
+            float *dst = static_cast<float *>(h->pinned_in[b].p);
+            h->pool->run([=](unsigned t, unsigned nt) {
+                const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
+                if (dtype == TM_F32) stage_rows_f32(reinterpret_cast<const float *>(csrc), row_stride, dst, r0, r1);
+                else stage_rows_f32(reinterpret_cast<const double *>(csrc), row_stride, dst, r0, r1);
+            });
             t_stage += now() - i0;
         }
         tmark(s_in);
-        TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, in_pinned ? static_cast<const void *>(csrc) : h->pinned_in[b].p, bytes,
+        TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, direct_in ? static_cast<const void *>(csrc) : h->pinned_in[b].p, bytes,
                                    cudaMemcpyHostToDevice, s_in));
         tmark(s_in);
         TM_CUDA(h, cudaEventRecord(h->pipe_event[EV_H2D + b], s_in));
         TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[EV_H2D + b], 0));
-        const float *pts32;
-        int64_t stride32;
-        if (dtype == TM_F64) {
-            float *conv = reinterpret_cast<float *>(h->chunk_in[b].as<unsigned char>() + in_bytes);
-            const int blocks = static_cast<int>(std::min<int64_t>((cnt * 3 + 255) / 256, static_cast<int64_t>(h->sm_count) * 32));
-            f64_to_f32_xyz_kernel<<<blocks, 256, 0, s_cmp>>>(h->chunk_in[b].as<double>(), cnt, row_stride, conv);
-            TM_CUDA(h, cudaGetLastError());
-            pts32 = conv;
-            stride32 = 3;
-        } else {
-            pts32 = h->chunk_in[b].as<float>();
-            stride32 = row_stride;
-        }
+        const float *pts32 = h->chunk_in[b].as<float>();
+        const int64_t stride32 = 3;
         h->stats = tm_stats{};
         const bool dev = on_device(c);
         LabelArgs a{pts32, cnt, stride32, *params, nullptr, dev ? h->chunk_id[b].as<int32_t>() : nullptr,
@@ -634,7 +644,7 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
         total.points_brute += h->stats.points_brute;
         h->last_n = cnt;
         if (dev) {
-            rc = tm_assemble_records(h, h->chunk_in[b].p, dtype, cnt, row_stride, h->chunk_off[b].as<float>(),
+            rc = tm_assemble_records(h, h->chunk_in[b].p, TM_F32, cnt, 3, h->chunk_off[b].as<float>(),
                                      h->chunk_id[b].as<int32_t>(), h->chunk_rec[b].as<double>(), s_cmp);
             if (rc != TM_OK) return rc;
         }
@@ -777,6 +787,18 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         }
         return TM_OK;
     };
+    // an error leaves copies of earlier chunks in flight into the caller's (or the staging) memory: wait for them before
+    // handing control back
+    auto bail = [&](int code) { cudaDeviceSynchronize(); return code; };
+#define TM_CUDA_BAIL(expr)                                                                                          \
+    do {                                                                                                            \
+        cudaError_t _e = (expr);                                                                                    \
+        if (_e != cudaSuccess) {                                                                                    \
+            cudaDeviceSynchronize();                                                                                \
+            return tmn::fail(h, _e == cudaErrorMemoryAllocation ? TM_ERR_NOMEM : TM_ERR_CUDA, "%s failed: %s", #expr, \
+                             cudaGetErrorString(_e));                                                               \
+        }                                                                                                           \
+    } while (0)
     for (int64_t c = 0; c < nchunks; ++c) {
         const int b = static_cast<int>(c & 1);
         const int64_t cnt = std::min(chunk, n - c * chunk);
@@ -785,25 +807,25 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         if (c >= 2) {
             // buffer b is being reused: its previous output must have left the device and the staging area
             rc = drain_out(c - 2);
-            if (rc != TM_OK) return rc;
-            TM_CUDA(h, cudaStreamWaitEvent(s_in, h->pipe_event[6 + b], 0));
+            if (rc != TM_OK) return bail(rc);
+            TM_CUDA_BAIL(cudaStreamWaitEvent(s_in, h->pipe_event[6 + b], 0));
         }
         if (!in_pinned) {
             par_memcpy(h->pinned_in[b].p, csrc, bytes);
-            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b].p, bytes, cudaMemcpyHostToDevice, s_in));
+            TM_CUDA_BAIL(cudaMemcpyAsync(h->chunk_in[b].p, h->pinned_in[b].p, bytes, cudaMemcpyHostToDevice, s_in));
         } else {
-            TM_CUDA(h, cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
+            TM_CUDA_BAIL(cudaMemcpyAsync(h->chunk_in[b].p, csrc, bytes, cudaMemcpyHostToDevice, s_in));
         }
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[0 + b], s_in));
-        TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[0 + b], 0));
-        if (c >= 2) TM_CUDA(h, cudaStreamWaitEvent(s_cmp, h->pipe_event[4 + b], 0));   // records buffer b free again
+        TM_CUDA_BAIL(cudaEventRecord(h->pipe_event[0 + b], s_in));
+        TM_CUDA_BAIL(cudaStreamWaitEvent(s_cmp, h->pipe_event[0 + b], 0));
+        if (c >= 2) TM_CUDA_BAIL(cudaStreamWaitEvent(s_cmp, h->pipe_event[4 + b], 0));   // records buffer b free again
         const float *pts32;
         int64_t stride32;
         if (dtype == TM_F64) {
             float *conv = reinterpret_cast<float *>(h->chunk_in[b].as<unsigned char>() + in_bytes);
             const int blocks = static_cast<int>(std::min<int64_t>((cnt * 3 + 255) / 256, static_cast<int64_t>(h->sm_count) * 32));
             f64_to_f32_xyz_kernel<<<blocks, 256, 0, s_cmp>>>(h->chunk_in[b].as<double>(), cnt, row_stride, conv);
-            TM_CUDA(h, cudaGetLastError());
+            TM_CUDA_BAIL(cudaGetLastError());
             pts32 = conv;
             stride32 = 3;
         } else {
@@ -814,32 +836,33 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
         LabelArgs a{pts32, cnt, stride32, *params, nullptr, h->chunk_id[b].as<int32_t>(),
                     out_dist_host ? h->chunk_dist[b].as<float>() : nullptr, h->chunk_off[b].as<float>(), nullptr, s_cmp};
         rc = label_dispatch(h, a);
-        if (rc != TM_OK) return rc;
+        if (rc != TM_OK) return bail(rc);
         total.pairs_evaluated += h->stats.pairs_evaluated;
         total.points_brute += h->stats.points_brute;
         total.mode_used = h->stats.mode_used;
         h->last_n = cnt;
         rc = tm_assemble_records(h, h->chunk_in[b].p, dtype, cnt, row_stride, h->chunk_off[b].as<float>(),
                                  h->chunk_id[b].as<int32_t>(), h->chunk_rec[b].as<double>(), s_cmp);
-        if (rc != TM_OK) return rc;
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[2 + b], s_cmp));
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[6 + b], s_cmp));
-        TM_CUDA(h, cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
+        if (rc != TM_OK) return bail(rc);
+        TM_CUDA_BAIL(cudaEventRecord(h->pipe_event[2 + b], s_cmp));
+        TM_CUDA_BAIL(cudaEventRecord(h->pipe_event[6 + b], s_cmp));
+        TM_CUDA_BAIL(cudaStreamWaitEvent(s_out, h->pipe_event[2 + b], 0));
         double *dst_rec = out_pinned ? out_records_host + c * chunk * 7 : static_cast<double *>(h->pinned_out[b].p);
-        TM_CUDA(h, cudaMemcpyAsync(dst_rec, h->chunk_rec[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double),
+        TM_CUDA_BAIL(cudaMemcpyAsync(dst_rec, h->chunk_rec[b].p, static_cast<size_t>(cnt) * 7 * sizeof(double),
                                    cudaMemcpyDeviceToHost, s_out));
         if (out_dist_host) {
             float *dst_d = out_pinned ? out_dist_host + c * chunk
                                       : reinterpret_cast<float *>(static_cast<unsigned char *>(h->pinned_out[b].p) + rec_bytes);
-            TM_CUDA(h, cudaMemcpyAsync(dst_d, h->chunk_dist[b].p, static_cast<size_t>(cnt) * sizeof(float),
+            TM_CUDA_BAIL(cudaMemcpyAsync(dst_d, h->chunk_dist[b].p, static_cast<size_t>(cnt) * sizeof(float),
                                        cudaMemcpyDeviceToHost, s_out));
         }
-        TM_CUDA(h, cudaEventRecord(h->pipe_event[4 + b], s_out));
+        TM_CUDA_BAIL(cudaEventRecord(h->pipe_event[4 + b], s_out));
     }
     for (int64_t c = std::max<int64_t>(0, nchunks - 2); c < nchunks; ++c) {
         rc = drain_out(c);
-        if (rc != TM_OK) return rc;
+        if (rc != TM_OK) return bail(rc);
     }
+#undef TM_CUDA_BAIL
     TM_CUDA(h, cudaStreamSynchronize(s_out));
     TM_CUDA(h, cudaStreamSynchronize(s_cmp));
     h->stats.pairs_evaluated = total.pairs_evaluated;
@@ -954,6 +977,36 @@ int tm_proximity_flags_host(tm_handle *h, const int64_t *subset_host, int64_t n,
     h->stats.mode_used = TM_MODE_BRUTE;
     h->stats.pairs_evaluated = static_cast<uint64_t>(n) * static_cast<uint64_t>(m);
     h->stats.points_brute = static_cast<uint64_t>(n);
+    return TM_OK;
+}
+
+int tm_measure_host_bandwidth(tm_handle *h, double *bytes_per_second, int32_t *threads) {
+    if (!h || !bytes_per_second) return TM_ERR_INVALID;
+    const unsigned nt = std::min(host_threads_available(), 16u);
+    if (!h->pool || h->pool->n != nt) {
+        delete h->pool;
+        h->pool = new (std::nothrow) tmn::HostPool(nt);
+        if (!h->pool) return tmn::fail(h, TM_ERR_NOMEM, "host worker pool%s%s");
+    }
+    const size_t words = (256u << 20) / sizeof(double);
+    std::vector<double> src(words, 1.0), dst(words);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const double *sp = src.data();
+        double *dp = dst.data();
+        h->pool->run([=](unsigned t, unsigned n) {
+            const size_t per = (words + n - 1) / n, lo = std::min(words, t * per), hi = std::min(words, lo + per);
+            for (size_t i = lo; i < hi; ++i) store_f64(dp + i, sp[i]);
+#if defined(__x86_64__)
+            _mm_sfence();
+#endif
+        });
+        const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        best = std::max(best, 2.0 * static_cast<double>(words) * sizeof(double) / s);
+    }
+    *bytes_per_second = best;
+    if (threads) *threads = static_cast<int32_t>(nt);
     return TM_OK;
 }
 

@@ -17,6 +17,8 @@ QSM_COLUMNS = ("startX", "startY", "startZ", "endX", "endY", "endZ", "radius", "
 # The objects are held strongly: an address can be recycled by the caching allocator the moment its tensor dies, so
 # only "the very same live tensor objects, unmodified, and nobody installed another table since" skips the install.
 _table_key: dict[int, tuple] = {}
+# device index -> ((variant, norm_fma, engine install counter), (M,7) float32 table, int32 IDs) of the last DataFrame install
+_frame_key: dict[int, tuple] = {}
 
 
 def _cuda_device(device) -> torch.device:
@@ -89,15 +91,23 @@ def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None,
     # single-column access: DataFrame[[...]] re-indexes and copies through a block manager (1.5 ms per call for nothing)
     def col(name, dtype=np.float32):
         return np.asarray(cylinders[name].to_numpy(), dtype=dtype)
-    start = torch.as_tensor(np.stack([col("startX"), col("startY"), col("startZ")], axis=1), device=dev)
-    end = torch.as_tensor(np.stack([col("endX"), col("endY"), col("endZ")], axis=1), device=dev)
-    radius = torch.as_tensor(col("radius"), device=dev)
-    ids = torch.as_tensor(np.asarray(cylinders["ID"].to_numpy()).astype(np.int32), device=dev)
-    m = start.shape[0]
+    table = np.stack([col("startX"), col("startY"), col("startZ"), col("endX"), col("endY"), col("endZ"), col("radius")], axis=1)
+    ids_np = np.asarray(cylinders["ID"].to_numpy()).astype(np.int32)
+    m = table.shape[0]
     norm_fma = m <= 1                        # DataFrame tensors are Fortran-ordered in the reference (strided norm)
-    length, unit = eng.prepare(start, end, variant, norm_fma=norm_fma)
-    eng.set_cylinders(start, radius, length, unit, ids)
-    _table_key.pop(dev.index, None)
+    # the same QSM again (augmented clouds of one tree, repeated calls): the table and its voxel index are still installed.
+    # Decided on the VALUES (a 1.6 MB comparison at 50k cylinders), never on object identity.
+    held = _frame_key.get(dev.index)
+    if not (held is not None and held[0] == (variant, norm_fma, eng.installs) and held[1].shape == table.shape
+            and np.array_equal(held[1], table, equal_nan=True) and np.array_equal(held[2], ids_np)):
+        start = torch.as_tensor(table[:, 0:3], device=dev)
+        end = torch.as_tensor(table[:, 3:6], device=dev)
+        radius = torch.as_tensor(table[:, 6], device=dev)
+        ids = torch.as_tensor(ids_np, device=dev)
+        length, unit = eng.prepare(start, end, variant, norm_fma=norm_fma)
+        eng.set_cylinders(start, radius, length, unit, ids)
+        _frame_key[dev.index] = ((variant, norm_fma, eng.installs), table, ids_np)
+        _table_key.pop(dev.index, None)
     cloud = np.asarray(cloud)
     if cloud.ndim != 2 or cloud.shape[1] < 3:
         raise ValueError(f"cloud must have shape (N, >=3), got {cloud.shape}")

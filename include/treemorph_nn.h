@@ -240,6 +240,13 @@ int tm_noise_cloud(tm_handle *h, const double *cyl_rec, const int64_t *first_poi
  */
 int tm_host_pipeline_info(tm_handle *h, int32_t *d2h_bytes_per_point, int32_t *host_threads);
 
+/*
+ * STREAM-style probe of the HOST memory system with the worker threads tm_label_cloud_host uses: copies a 256 MiB
+ * buffer (plain loads, streaming stores) a few times and reports (bytes read + bytes written) per second of the best
+ * pass.  bench.py quotes the end-to-end call's host traffic against it.  No device work.
+ */
+int tm_measure_host_bandwidth(tm_handle *h, double *bytes_per_second, int32_t *threads);
+
 /* Counters of the last labelling call.  Synchronises the device. */
 int tm_get_stats(tm_handle *h, tm_stats *out);
 

@@ -369,7 +369,8 @@ def test_host_pipeline_variants_agree(eng, f64, monkeypatch):
             monkeypatch.setenv("TM_HOST_SPLIT", split)
         out = torch.full((len(pts), 7), -1.0, dtype=torch.float64).pin_memory().numpy()
         rec, dist = eng.label_cloud_host(cloud, api.VARIANT_B, mode="grid", want_dist=True, out=out)
-        assert rec is out and abs(eng.host_pipeline_info()["d2h_bytes_per_point"] - per_point) <= 6
+        want = 20 if f64 else per_point              # float64 clouds: the device only has their float32 rounding, hosts assemble all
+        assert rec is out and abs(eng.host_pipeline_info()["d2h_bytes_per_point"] - want) <= 6
         assert np.array_equal(rec, outs["0"][0], equal_nan=True) and np.array_equal(dist, ora["dist"], equal_nan=True)
     for pinned in ("1", "0"):                                                # result array allocated by the engine
         monkeypatch.setenv("TM_PINNED_OUT", pinned)
