@@ -125,7 +125,7 @@ finalize_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, co
     const int64_t n_eff = d_count ? static_cast<int64_t>(*d_count) : n;
     for (int64_t slot = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; slot < n_eff;
          slot += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t row = sel ? static_cast<int64_t>(sel[slot] & 0x7fffffff) : slot;   // sign bit: "outside the grid" flag
+        const int64_t row = sel ? static_cast<int64_t>(sel[slot] & 0x3fffffff) : slot;   // sign bit: "outside the grid" flag
         const uint32_t j = key_index(keys[slot]);
         const float *p = pts + row * row_stride;
         const float px = p[0], py = p[1], pz = p[2];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) brute_cull_kernel(BruteCullArgs a) {
          task += nwarps) {
         const unsigned int slot = a.brute_slots[static_cast<unsigned int>(task / nchunks)];
         const int chunk = static_cast<int>(task % nchunks);
-        const float *p = a.pts + static_cast<int64_t>(a.pend_idx[slot] & 0x7fffffff) * a.row_stride;
+        const float *p = a.pts + static_cast<int64_t>(a.pend_idx[slot] & 0x3fffffff) * a.row_stride;
         const float px = p[0], py = p[1], pz = p[2];
         // rounding allowance at this point's own coordinate scale (inf / NaN coordinates: nothing is culled)
         const float slack = a.slack_floor + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
@@ -312,12 +312,16 @@ int label_brute(tm_handle *h, const LabelArgs &a) {
     return TM_OK;
 }
 
-// winning rows of the pending slots (tree search and exhaustive alike) -> win[original row]
-__global__ void __launch_bounds__(256) pending_winner_kernel(const int32_t *__restrict__ pend_idx, const unsigned int *__restrict__ d_count,
+// winning rows of the pending slots the exhaustive kernel settled (non-finite points) -> win[original row]; the ring and
+// tree searches write theirs themselves
+__global__ void __launch_bounds__(256) pending_winner_kernel(const int32_t *__restrict__ pend_idx, const uint32_t *__restrict__ brute_slots,
+                                                             const unsigned int *__restrict__ d_count,
                                                              const unsigned long long *__restrict__ keys, int32_t *__restrict__ win) {
     const unsigned int n = *d_count;
-    for (unsigned int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x)
-        win[pend_idx[slot] & 0x7fffffff] = static_cast<int32_t>(key_index(keys[slot]));
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int slot = brute_slots[k];
+        win[pend_idx[slot] & 0x3fffffff] = static_cast<int32_t>(key_index(keys[slot]));
+    }
 }
 
 // Streaming winner-only epilogue (A:92-109) over the rows in input order: recompute the winning pair with full geometry
@@ -402,13 +406,14 @@ int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win
     b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = maxabs; b.slack_floor = h->slack_floor;
     b.keys = h->keys.as<unsigned long long>();
     b.st = dst;
-    const int wgrid = h->sm_count * 8;
+    // non-finite points are rare: a small grid, and grid-stride loops if there are many after all
+    const int wgrid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(h->sm_count) * 8, std::max<int64_t>(h->sm_count / 2, a.n / 4096)));
     if (guard) { if (nfma) brute_cull_kernel<true, true><<<wgrid, 256, 0, a.stream>>>(b); else brute_cull_kernel<true, false><<<wgrid, 256, 0, a.stream>>>(b); }
     else       { if (nfma) brute_cull_kernel<false, true><<<wgrid, 256, 0, a.stream>>>(b); else brute_cull_kernel<false, false><<<wgrid, 256, 0, a.stream>>>(b); }
     TM_KCHECK(h, a.stream, "brute_cull_kernel");
     mark(h, 6, a.stream);
-    pending_winner_kernel<<<h->sm_count * 4, 256, 0, a.stream>>>(h->pend_idx.as<int32_t>(), &dst->pending,
-                                                                h->keys.as<unsigned long long>(), win);
+    pending_winner_kernel<<<std::max(1, wgrid / 8), 256, 0, a.stream>>>(h->pend_idx.as<int32_t>(), h->brute_slots.as<uint32_t>(), &dst->n_brute,
+                                                                       h->keys.as<unsigned long long>(), win);
     TM_KCHECK(h, a.stream, "pending_winner_kernel");
     return TM_OK;
 }

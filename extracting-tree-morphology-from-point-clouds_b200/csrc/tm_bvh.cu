@@ -198,7 +198,7 @@ struct BvhArgs {
     const int32_t *pend_idx;
     unsigned long long *pend_keys;
     const unsigned int *d_pending;
-    const uint8_t *pend_done;      // slots the ring search has already certified
+    int32_t *win;                  // winning row of every slot this kernel settles, at the point's row
     const BvhNode *nodes;
     const float4 *leafAB;
     const int32_t *leaf_rows;
@@ -227,6 +227,7 @@ __device__ __forceinline__ float box_dist2(float px, float py, float pz, const f
 //     lanes (5.6 of 32 lanes active on average, profiles/r01i_tree_search.md).
 constexpr int BVH_NODE_STEPS = 6;
 constexpr int32_t BVH_IDLE = 0x7fffffff;
+constexpr int32_t BVH_DONE_BIT = 0x40000000;      // tm_grid.cu: DONE_BIT of a pending slot
 
 template <bool GUARD, bool NFMA>
 __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
     int sp = 0;
     int32_t node = BVH_IDLE;            // BVH_IDLE: no point in flight; >= 0: inner node to visit; < 0: leaf to visit
     unsigned int slot = 0;
+    int32_t row = 0;
     float px = 0.f, py = 0.f, pz = 0.f, slack = 0.f, thr = 0.f;
     unsigned long long key = KEY_NONE;
     bool more = n_pend > 0;             // warp-uniform: slots left to hand out
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
             if (!(stk_d2[sp] > thr * thr)) { node = stk_node[sp]; return; }
         }
         a.pend_keys[slot] = key;
+        a.win[row] = static_cast<int32_t>(key_index(key));
         node = BVH_IDLE;
     };
 
@@ -264,14 +267,16 @@ __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (base + static_cast<unsigned int>(__popc(want)) >= n_pend) more = false;
                 const unsigned int s = base + static_cast<unsigned int>(__popc(want & lt));
-                if (node == BVH_IDLE && s < n_pend && !a.pend_done[s]) {
-                    const int32_t ri = a.pend_idx[s];
-                    const float *p = a.pts + static_cast<int64_t>(ri & 0x7fffffff) * a.row_stride;
+                const int32_t ri = (node == BVH_IDLE && s < n_pend) ? a.pend_idx[s] : BVH_DONE_BIT;
+                if (!(ri & BVH_DONE_BIT)) {
+                    const int32_t my_row = ri & 0x3fffffff;
+                    const float *p = a.pts + static_cast<int64_t>(my_row) * a.row_stride;
                     px = p[0]; py = p[1]; pz = p[2];
                     key = a.pend_keys[s];
                     // non-finite points are the exhaustive kernel's; a NaN incumbent is final
                     if (fabsf(px) + fabsf(py) + fabsf(pz) < 3.0e38f && static_cast<uint32_t>(key >> 32) != 0u) {
                         slot = s;
+                        row = my_row;
                         slack = a.slack_floor + 4e-6f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), a.maxabs));
                         if (ri < 0) {
                             // outside the grid: the tile kernel never saw this point
@@ -299,6 +304,7 @@ __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
                             node = a.root;
                         } else {
                             a.pend_keys[s] = key;
+                            a.win[my_row] = static_cast<int32_t>(key_index(key));
                         }
                     }
                 }
@@ -350,6 +356,7 @@ __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
             }
             if (static_cast<uint32_t>(key >> 32) == 0u) {       // NaN: nothing can beat it
                 a.pend_keys[slot] = key;
+                a.win[row] = static_cast<int32_t>(key_index(key));
                 node = BVH_IDLE;
             } else {
                 pop();
@@ -367,13 +374,13 @@ __global__ void __launch_bounds__(128, 12) bvh_kernel(BvhArgs a) {
     }
 }
 
-int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst) {
+int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win) {
     BvhArgs b;
     b.pts = a.pts; b.row_stride = a.row_stride;
     b.pend_idx = h->pend_idx.as<int32_t>();
     b.pend_keys = h->keys.as<unsigned long long>();
     b.d_pending = &dst->pending;
-    b.pend_done = h->pend_done.as<uint8_t>();
+    b.win = win;
     b.nodes = h->bvh_nodes.as<BvhNode>();
     b.leafAB = h->bvh_leafAB.as<float4>();
     b.leaf_rows = h->bvh_rows.as<int32_t>();
@@ -384,7 +391,8 @@ int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst) {
     b.atol = a.prm.perp_atol; b.eps = a.prm.norm_eps; b.maxabs = h->maxabs; b.slack_floor = h->slack_floor;
     b.st = dst;
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
-    const int grid = h->sm_count * 12;
+    // one lane per pending point: small calls get a small grid
+    const int grid = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(h->sm_count) * 12, std::max<int64_t>(h->sm_count, a.n / 2048)));
     if (guard) { if (nfma) bvh_kernel<true, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<true, false><<<grid, 128, 0, a.stream>>>(b); }
     else       { if (nfma) bvh_kernel<false, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<false, false><<<grid, 128, 0, a.stream>>>(b); }
     TM_KCHECK(h, a.stream, "bvh_kernel");

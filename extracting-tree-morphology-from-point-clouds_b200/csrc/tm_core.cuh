@@ -149,7 +149,6 @@ struct tm_handle {
     tmn::DevBuf tile_desc;           // uint4 per voxel code {tile offset, near length, tile length, 0} (static, per table)
     tmn::DevBuf pend_idx;            // int32 original row per pending slot (sign bit: outside the grid)
     tmn::DevBuf brute_slots;         // uint32 pending slots that need the exhaustive kernel
-    tmn::DevBuf pend_done;           // uint8 per pending slot: 1 = final after the ring search
     tmn::DevBuf win;                 // int32 per point: winning cylinder row (when the caller passes no out_index)
     tmn::DevBuf dstats;              // tmn::DevStats + cursors
     tmn::DevBuf scratch_f;           // misc float scratch
@@ -261,7 +260,7 @@ int run_proximity(tm_handle *h, const SmallArgs &a, bool guard, bool nfma, cudaS
 int exclusive_scan_u32(tm_handle *h, const uint32_t *count, uint32_t n, uint32_t *start, cudaStream_t stream);
 // tm_bvh.cu
 int build_bvh(tm_handle *h, cudaStream_t stream, int n_regular, const float *lo, const float *hi);
-int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst);
+int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win);
 // tm_grid.cu
 int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream);
 int label_grid(tm_handle *h, const LabelArgs &a);

@@ -618,6 +618,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t NO_CELL = 0xFFFFFFFFu;
 constexpr int32_t OUTSIDE_BIT = static_cast<int32_t>(0x80000000u);
+constexpr int32_t DONE_BIT = 0x40000000;          // pending slot already final (set by the ring search); rows stay below 2^30
 
 // pass 1: voxel occupancy.  The atomics return nothing (RED): no per-point state is kept between the passes, the
 // scatter pass recomputes the voxel id from the coordinates (cheaper than 8 bytes of HBM traffic per point each way).
@@ -814,7 +815,11 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
     StageScratch &sg = stage[threadIdx.x >> 5];
     const uint32_t n_items = a.st->work_items, total_slots = a.st->lane_slots;
     const uint32_t n_wslots = (total_slots + 31u) >> 5;
-    const uint32_t n_chunks = (n_wslots + EV_CHUNK_ROUNDS - 1u) / EV_CHUNK_ROUNDS;
+    // consecutive rounds per cursor fetch: 4 when every warp still gets several chunks, fewer for small clouds (a warp
+    // runs its rounds one after the other: short calls want them spread over all warps)
+    const uint32_t n_warps = gridDim.x * EV_WARPS;
+    const uint32_t chunk_rounds = n_wslots >= 16u * n_warps ? EV_CHUNK_ROUNDS : (n_wslots >= 4u * n_warps ? 2u : 1u);
+    const uint32_t n_chunks = (n_wslots + chunk_rounds - 1u) / chunk_rounds;
     const uint32_t n_sorted = static_cast<uint32_t>(a.st->points_binned);
     const float S = a.amb;
     const float band_hi = a.atol + S, band_lo = a.atol - S, rho2_min = S * S;
@@ -854,8 +859,8 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
     uint32_t chunk = fetch();
     while (chunk < n_chunks) {
         const uint32_t next_chunk = fetch();
-        const uint32_t r_end = min((chunk + 1u) * EV_CHUNK_ROUNDS, n_wslots);
-        for (uint32_t cur = chunk * EV_CHUNK_ROUNDS; cur < r_end; ++cur) {
+        const uint32_t r_end = min((chunk + 1u) * chunk_rounds, n_wslots);
+        for (uint32_t cur = chunk * chunk_rounds; cur < r_end; ++cur) {
             // ---- which voxel run does this lane's slot belong to?  The warp's 32 slots span at most 32 consecutive items.
             const uint32_t it0 = a.warp_item[cur];
             const uint32_t mine = it0 + lane < n_items ? a.items2[it0 + lane].y : 0xFFFFFFFFu;
@@ -893,7 +898,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
                 constexpr uint32_t RP = 32 * PTS_PER_LANE;                  // points per round, at most
                 const uint32_t p_end = __reduce_max_sync(0xffffffffu, valid ? p0 + PTS_PER_LANE : 0u);
                 const uint32_t i_end = __reduce_max_sync(0xffffffffu, valid ? item : 0u);
-                const uint32_t p_from = p_end + (cur == chunk * EV_CHUNK_ROUNDS ? 0u : RP);       // first round of a chunk: both
+                const uint32_t p_from = p_end + (cur == chunk * chunk_rounds ? 0u : RP);       // first round of a chunk: both
                 if (lane < RP / 4) { if (p_from + 8u * lane < n_sorted) prefetch_l1(a.sorted + p_from + 8u * lane); }
                 if (lane >= 16 && lane < 20) { if (i_end + 8u * (lane - 16u) < n_items) prefetch_l1(a.items + i_end + 8u * (lane - 16u)); }
                 else if (lane >= 20 && lane < 22) { if (i_end + 16u * (lane - 20u) < n_items) prefetch_l1(a.items2 + i_end + 16u * (lane - 20u)); }
@@ -1298,9 +1303,9 @@ constexpr int RING_WARPS = 4;
 struct RingArgs {
     const float *pts;
     int64_t row_stride;
-    const int32_t *pend_idx;
+    int32_t *pend_idx;             // DONE_BIT is set on the slots the ring search certifies (the tree search skips them)
     unsigned long long *pend_keys;
-    uint8_t *pend_done;            // 1 = this slot is final (the tree search skips it)
+    int32_t *win;
     const uint32_t *tile_start, *tile_cnt;
     const float4 *tileAB;
     const int32_t *tileI;
@@ -1440,7 +1445,11 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
         }
         if (tid == 0) {
             a.pend_keys[task] = key;                 // certified or not, the incumbent seeds whatever comes next
-            if (certified) { a.pend_done[task] = 1; atomicAdd(&a.st->ring_certified, 1u); }
+            if (certified) {
+                a.pend_idx[task] = ri | DONE_BIT;
+                a.win[ri] = static_cast<int32_t>(key_index(key));
+                atomicAdd(&a.st->ring_certified, 1u);
+            }
         }
     }
 #pragma unroll
@@ -1477,8 +1486,6 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     TM_CUDA(h, h->undecided.ensure(sizeof(uint4) * n));
     TM_CUDA(h, h->late_rows.ensure(sizeof(uint32_t) * n));
     TM_CUDA(h, h->dstats.ensure(sizeof(DevStats) + 64));
-    TM_CUDA(h, h->pend_done.ensure(n));
-    TM_CUDA(h, cudaMemsetAsync(h->pend_done.p, 0, n, st));
     DevStats *dst = h->dstats.as<DevStats>();
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
     mark(h, 1, st); mark(h, 2, st); mark(h, 3, st);
@@ -1535,16 +1542,17 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     rg.pts = a.pts; rg.row_stride = a.row_stride;
     rg.pend_idx = h->pend_idx.as<int32_t>();
     rg.pend_keys = h->keys.as<unsigned long long>();
-    rg.pend_done = h->pend_done.as<uint8_t>();
+    rg.win = win;
     rg.tile_start = h->cyl_cell_start.as<uint32_t>(); rg.tile_cnt = h->cyl_cell_cnt.as<uint32_t>();
     rg.tileAB = h->tileAB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
     rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
     rg.st = dst;
-    const int rg_blocks = h->sm_count * (2048 / (RING_WARPS * 32));
+    // one CTA per pending point; far fewer points than rows ever reach it, so small calls get a small grid
+    const int rg_blocks = static_cast<int>(std::min<size_t>(static_cast<size_t>(h->sm_count) * (2048 / (RING_WARPS * 32)), std::max<size_t>(h->sm_count, n / 256)));
     if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
-    int rc = search_bvh(h, a, dst);
+    int rc = search_bvh(h, a, dst, win);
     if (rc != TM_OK) return rc;
     mark(h, 5, st);
     rc = finish_pending(h, a, dst, win, h->maxabs);
@@ -1556,7 +1564,7 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
 
 int label_grid(tm_handle *h, const LabelArgs &a) {
     if (a.n == 0) return TM_OK;
-    if (a.n > 0x7fffffffLL) return fail(h, TM_ERR_INVALID, "tm_label_points: more than 2^31-1 points per call%s%s");
+    if (a.n >= 0x40000000LL) return fail(h, TM_ERR_INVALID, "tm_label_points: more than 2^30-1 points per call%s%s");
     cudaStream_t st = a.stream;
     const float want_cell = a.prm.cell_size > 0.f ? a.prm.cell_size : auto_cell_size(h, a.n);
     if (!h->have_grid || h->grid_cell != want_cell) {
@@ -1594,8 +1602,6 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     TM_CUDA(h, h->keys.ensure(sizeof(unsigned long long) * n));
     if (!a.out_index) TM_CUDA(h, h->win.ensure(sizeof(int32_t) * n));
     TM_CUDA(h, h->dstats.ensure(sizeof(DevStats) + 64));
-    TM_CUDA(h, h->pend_done.ensure(n));
-    TM_CUDA(h, cudaMemsetAsync(h->pend_done.p, 0, n, st));
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
@@ -1662,16 +1668,17 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     rg.pts = a.pts; rg.row_stride = a.row_stride;
     rg.pend_idx = h->pend_idx.as<int32_t>();
     rg.pend_keys = h->keys.as<unsigned long long>();
-    rg.pend_done = h->pend_done.as<uint8_t>();
+    rg.win = win;
     rg.tile_start = h->cyl_cell_start.as<uint32_t>(); rg.tile_cnt = h->cyl_cell_cnt.as<uint32_t>();
     rg.tileAB = h->tileAB.as<float4>(); rg.tileI = h->tileI.as<int32_t>();
     rg.atol = a.prm.perp_atol; rg.eps = a.prm.norm_eps;
     rg.st = dst;
-    const int rg_blocks = h->sm_count * (2048 / (RING_WARPS * 32));
+    // one CTA per pending point; far fewer points than rows ever reach it, so small calls get a small grid
+    const int rg_blocks = static_cast<int>(std::min<size_t>(static_cast<size_t>(h->sm_count) * (2048 / (RING_WARPS * 32)), std::max<size_t>(h->sm_count, n / 256)));
     if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
-    rc = search_bvh(h, a, dst);
+    rc = search_bvh(h, a, dst, win);
     if (rc != TM_OK) return rc;
 
     // exhaustive search for non-finite points, then the winning rows of every pending point
