@@ -102,8 +102,8 @@ class ClockSampler:
         if self.nvml is None:
             return self._smi_once()
         inside = [(c, r) for ts, c, r in self.rows if t0 <= ts <= t1]
-        if not inside:                        # region shorter than one poll: nearest samples
-            inside = [(c, r) for _, c, r in sorted(self.rows, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:3]]
+        if len(inside) < 3:                   # region shorter than a few polls: add the nearest samples around it
+            inside = [(c, r) for _, c, r in sorted(self.rows, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:5]]
         reasons = sorted(name for name, bit in self.REASONS.items() if any(r & bit for _, r in inside))
         return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.smax,
                 "reasons": reasons, "samples": len(inside), "source": "NVML polled every 1 ms during the timed region"}

@@ -743,6 +743,7 @@ struct EvalArgs {
     const float *tileLB;
     float atol, eps, slack, near, reach;
     float amb;                    // S of the estimate comparison (<= slack)
+    int pf;                       // L1 prefetch switches (experiments): 1 own tile, 2 next round's points / items, 4 tiles ahead
     uint4 *undecided;             // points the estimates could not decide: {sorted position, item, bits(upper bound), 0};
     uint32_t undecided_cap;       //   near-certified ones fill the array from the front, the others from the back
     int32_t *win;                 // winning cylinder row of every certified point, at the point's original row
@@ -885,7 +886,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
             const float4 *tile = a.tileAB + 2 * static_cast<size_t>(tile_off);
             // the lane's tile is read entry by entry below: ask for all of its 128-byte lines now (lanes of one voxel ask
             // for the same lines), so that the loop finds them in L1 instead of paying the L2 latency once per entry
-            for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
+            if (a.pf & 1) for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
             float4 P[PTS_PER_LANE];
             P[0] = pv[0] ? a.sorted[p0] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
             // their lines can be asked for now (no address depends on anything still in flight) — points two rounds ahead,
             // item records one round ahead, and the tiles of the next few items as soon as their records are here (below)
             uint2 ahead = make_uint2(0u, 0u);
-            if (cur + 1u < r_end) {
+            if ((a.pf & 2) && cur + 1u < r_end) {
                 constexpr uint32_t RP = 32 * PTS_PER_LANE;                  // points per round, at most
                 const uint32_t p_end = __reduce_max_sync(0xffffffffu, valid ? p0 + PTS_PER_LANE : 0u);
                 const uint32_t i_end = __reduce_max_sync(0xffffffffu, valid ? item : 0u);
@@ -902,7 +903,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
                 if (lane < RP / 4) { if (p_from + 8u * lane < n_sorted) prefetch_l1(a.sorted + p_from + 8u * lane); }
                 if (lane >= 16 && lane < 20) { if (i_end + 8u * (lane - 16u) < n_items) prefetch_l1(a.items + i_end + 8u * (lane - 16u)); }
                 else if (lane >= 20 && lane < 22) { if (i_end + 16u * (lane - 20u) < n_items) prefetch_l1(a.items2 + i_end + 16u * (lane - 20u)); }
-                else if (lane >= 22 && lane < 28) { if (i_end + (lane - 21u) < n_items) { const uint4 nx = a.items[i_end + (lane - 21u)]; ahead = make_uint2(nx.x, nx.y); } }
+                else if ((a.pf & 4) && lane >= 22 && lane < 28) { if (i_end + (lane - 21u) < n_items) { const uint4 nx = a.items[i_end + (lane - 21u)]; ahead = make_uint2(nx.x, nx.y); } }
             }
 
             // ---- estimates over the near part of the lane's own tile, entries double-buffered in registers
@@ -987,6 +988,158 @@ struct __align__(16) ExactScratch {
     uint2 q[Q_CAP];                           // {pool position (or row | Q_REC), lane of the point}
 };
 
+template <bool GUARD, bool NFMA>
+__device__ __forceinline__ void exact_drain(const EvalArgs &a, ExactScratch &ws, uint32_t lane, uint32_t &qn, unsigned int &pairs) {
+    __syncwarp();
+    const uint32_t n = min(qn, 32u);
+    if (lane < n) {
+        const uint2 e = ws.q[qn - n + lane];
+        const float4 P = ws.P[e.y];
+        float4 ca, cb;
+        uint32_t ci;
+        if (e.x & Q_REC) { ci = e.x & ~Q_REC; ca = a.recA[ci]; cb = a.recB[ci]; }
+        else { ca = a.tileAB[2 * static_cast<size_t>(e.x)]; cb = a.tileAB[2 * static_cast<size_t>(e.x) + 1]; ci = static_cast<uint32_t>(a.tileI[e.x]); }
+        const float d = eval_pair<GUARD, NFMA, false>(P.x, P.y, P.z, ca, cb, a.atol, a.eps, nullptr);
+        atomicMin(&ws.best[e.y], make_key(d, ci));
+    }
+    qn -= n;
+    pairs += n;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void exact_push(ExactScratch &ws, uint32_t lt, bool hit, uint32_t pos, uint32_t slot, uint32_t &qn) {
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        if (hit) ws.q[qn + __popc(m & lt)] = make_uint2(pos, slot);
+        qn += __popc(m);
+    }
+}
+
+// One task = 32 / GS undecided points, GS lanes per point.  GS = 1: every lane walks its own point's tile (the short walks
+// of the near-certified points); GS = 8: eight lanes step through a point's tile together (the noise tail walks the whole
+// far part, often hundreds of entries: eight times fewer dependent steps per point).
+template <bool GUARD, bool NFMA, bool DIRECT, int GS>
+__device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, uint32_t lane, uint32_t lt, uint32_t task,
+                                           bool is_front, uint32_t count, uint32_t &qn, unsigned int &pairs,
+                                           unsigned int &culls, unsigned int &nfar) {
+    constexpr uint32_t PW = 32 / GS;
+    const uint32_t g = lane / GS, sub = lane % GS;
+    const uint32_t leader = lane - sub;
+    const float INF = __int_as_float(0x7f800000);
+    const uint32_t idx = task * PW + g;
+    const bool valid = idx < count;
+    const uint4 rec = valid ? a.undecided[is_front ? idx : a.undecided_cap - 1u - idx] : make_uint4(0, 0, 0, 0);
+    float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t off = 0, total = 0;
+    if (valid) {
+        if (DIRECT) {
+            const float *p = a.pts + static_cast<int64_t>(rec.x) * a.row_stride;
+            P = make_float4(p[0], p[1], p[2], __uint_as_float(rec.x));
+            const uint4 d = a.tile_desc[rec.y];
+            off = d.x;
+            total = is_front ? d.y : d.z;
+        } else {
+            P = a.sorted[rec.x];
+            const uint4 it = a.items[rec.y];
+            off = it.x;
+            total = is_front ? it.y : it.y + a.items2[rec.y].x;
+        }
+    }
+    float thr = __uint_as_float(rec.z);            // NaN without a reliable estimate: nothing is culled
+    // the walk below reads the tile entry by entry: ask for the first lines now, the rest as the walk advances
+    if (total) {
+        if (sub == 0) prefetch_l1(a.tileLB + off);
+        for (uint32_t e = 4 * sub; e < min(total, 32u); e += 4 * GS) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + e));
+    }
+    if (sub == 0) { ws.P[g] = P; ws.best[g] = KEY_NONE; }
+    __syncwarp();
+    bool cut = false;                              // uniform within the group
+    uint32_t live = __ballot_sync(0xffffffffu, total > 0u);
+    for (uint32_t base = 0; live; base += GS) {
+        const uint32_t j = base + sub;
+        bool hit = false;
+        float lb = INF;
+        if (!cut && j < total) {
+            if ((j & 3u) == 0u && j + 32u < total) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + j + 32u));
+            if ((j & 31u) == 0u && j + 64u < total) prefetch_l1(a.tileLB + off + j + 64u);
+            lb = a.tileLB[off + j];
+        }
+        // the group's first entry of this step beyond the incumbent: everything from here on is farther
+        const float lb0 = GS == 1 ? lb : __shfl_sync(0xffffffffu, lb, leader);
+        if (!cut && base < total && lb0 > thr) cut = true;
+        if (!cut && j < total && !(lb > thr)) {
+            const float4 ca = a.tileAB[2 * static_cast<size_t>(off + j)], cb = a.tileAB[2 * static_cast<size_t>(off + j) + 1];
+            hit = cull_pass(P.x, P.y, P.z, ca, cb, thr);
+            ++culls;
+        }
+        exact_push(ws, lt, hit, off + j, g, qn);
+        if (qn >= 32u) {
+            exact_drain<GUARD, NFMA>(a, ws, lane, qn, pairs);
+            thr = fminf(thr, thr_of(ws.best[g], a.slack));     // fminf ignores a NaN operand
+        }
+        live = __ballot_sync(0xffffffffu, !cut && base + GS < total);
+    }
+    // cylinders that cannot be bounded (non-finite / non-unit axis): evaluated for every point; cylinders spanning too
+    // many voxels to be listed: cull test; variant A: points exactly on the axis line of an axis-parallel cylinder get
+    // NaN from it (and NaN wins)
+    for (uint32_t e0 = 0; e0 < a.n_special; e0 += GS) {
+        const uint32_t e = e0 + sub;
+        exact_push(ws, lt, valid && e < a.n_special, e < a.n_special ? (static_cast<uint32_t>(a.special[e]) | Q_REC) : 0u, g, qn);
+        while (qn >= 32u) exact_drain<GUARD, NFMA>(a, ws, lane, qn, pairs);
+    }
+    if (a.n_long) {
+        while (qn) exact_drain<GUARD, NFMA>(a, ws, lane, qn, pairs);
+        thr = fminf(thr, thr_of(ws.best[g], a.slack));
+        for (uint32_t e0 = 0; e0 < a.n_long; e0 += GS) {
+            const uint32_t e = e0 + sub;
+            bool hit = false;
+            uint32_t ci = 0;
+            if (valid && e < a.n_long) {
+                ci = static_cast<uint32_t>(a.long_list[e]);
+                hit = cull_pass(P.x, P.y, P.z, a.recA[ci], a.recB[ci], thr);
+                ++culls;
+            }
+            exact_push(ws, lt, hit, ci | Q_REC, g, qn);
+            while (qn >= 32u) exact_drain<GUARD, NFMA>(a, ws, lane, qn, pairs);
+        }
+    }
+    if (!GUARD) {
+        for (uint32_t e0 = 0; e0 < a.n_aligned; e0 += GS) {
+            const uint32_t e = e0 + sub;
+            bool hit = false;
+            uint32_t ci = 0;
+            if (valid && e < a.n_aligned) {
+                ci = static_cast<uint32_t>(a.aligned[e]);
+                hit = on_axis_line(P.x, P.y, P.z, a.recA[ci], a.recB[ci]);
+            }
+            exact_push(ws, lt, hit, ci | Q_REC, g, qn);
+            while (qn >= 32u) exact_drain<GUARD, NFMA>(a, ws, lane, qn, pairs);
+        }
+    }
+    while (qn) exact_drain<GUARD, NFMA>(a, ws, lane, qn, pairs);
+    const unsigned long long key = ws.best[g];
+    thr = fminf(thr, thr_of(key, a.slack));
+    // NaN incumbent (hi word 0) is final: NaN beats everything.  Near-certified: the exact distance is inside D_near.
+    // Otherwise: an entry beyond the incumbent ended the walk, or the whole tile was searched and the incumbent is
+    // inside D_max — everything else is farther.  KEY_NONE is never certified.
+    const bool mine = valid && sub == 0;
+    const bool nan_key = static_cast<uint32_t>(key >> 32) == 0u;
+    const bool near_ok = thr_of(key, a.slack) <= a.near;
+    const bool far_ok = !is_front && key != KEY_NONE && (cut || thr <= a.reach);
+    const bool done = mine && (nan_key || near_ok || far_ok);
+    if (done) a.win[__float_as_int(P.w)] = static_cast<int32_t>(key_index(key));
+    nfar += __popc(__ballot_sync(0xffffffffu, done && !nan_key && !near_ok));
+    const bool pend = mine && !done;
+    const uint32_t sp = warp_append(pend, &a.st->pending, lane, lt);
+    if (pend) {
+        a.pend_idx[sp] = __float_as_int(P.w);
+        a.pend_keys[sp] = key;
+    }
+    __syncwarp();                    // ws.P / ws.best are rewritten by the next task
+}
+
+constexpr int EXACT_FAR_LANES = 8;
+
 template <bool GUARD, bool NFMA, bool DIRECT>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
     __shared__ ExactScratch scratch[EV_WARPS];
@@ -994,134 +1147,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
     const uint32_t lt = (1u << lane) - 1u;
     ExactScratch &ws = scratch[warp];
     const uint32_t n_front = a.st->undecided_near, n_back = a.st->undecided_far;
-    const uint32_t w_front = (n_front + 31u) >> 5, w_all = w_front + ((n_back + 31u) >> 5);
-    const float INF = __int_as_float(0x7f800000);
+    constexpr uint32_t PB = 32 / EXACT_FAR_LANES;
+    const uint32_t w_front = (n_front + 31u) >> 5, w_all = w_front + (n_back + PB - 1u) / PB;
     unsigned int pairs = 0, culls = 0, nfar = 0;
     uint32_t qn = 0;
-
-    auto drain = [&]() {
-        __syncwarp();
-        const uint32_t n = min(qn, 32u);
-        if (lane < n) {
-            const uint2 e = ws.q[qn - n + lane];
-            const float4 P = ws.P[e.y];
-            float4 ca, cb;
-            uint32_t ci;
-            if (e.x & Q_REC) { ci = e.x & ~Q_REC; ca = a.recA[ci]; cb = a.recB[ci]; }
-            else { ca = a.tileAB[2 * static_cast<size_t>(e.x)]; cb = a.tileAB[2 * static_cast<size_t>(e.x) + 1]; ci = static_cast<uint32_t>(a.tileI[e.x]); }
-            const float d = eval_pair<GUARD, NFMA, false>(P.x, P.y, P.z, ca, cb, a.atol, a.eps, nullptr);
-            atomicMin(&ws.best[e.y], make_key(d, ci));
-        }
-        qn -= n;
-        pairs += n;
-        __syncwarp();
-    };
-    auto push = [&](bool hit, uint32_t pos) {
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            if (hit) ws.q[qn + __popc(m & lt)] = make_uint2(pos, lane);
-            qn += __popc(m);
-        }
-        return m != 0u;
-    };
-
+    // the long walks first: they are the critical path of a small call
     for (uint32_t w = blockIdx.x * EV_WARPS + warp; w < w_all; w += gridDim.x * EV_WARPS) {
-        const bool is_front = w < w_front;
-        const uint32_t idx = (is_front ? w : w - w_front) * 32u + lane;
-        const bool valid = idx < (is_front ? n_front : n_back);
-        const uint4 rec = valid ? a.undecided[is_front ? idx : a.undecided_cap - 1u - idx] : make_uint4(0, 0, 0, 0);
-        float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t off = 0, total = 0;
-        if (valid) {
-            if (DIRECT) {
-                const float *p = a.pts + static_cast<int64_t>(rec.x) * a.row_stride;
-                P = make_float4(p[0], p[1], p[2], __uint_as_float(rec.x));
-                const uint4 d = a.tile_desc[rec.y];
-                off = d.x;
-                total = is_front ? d.y : d.z;
-            } else {
-                P = a.sorted[rec.x];
-                const uint4 it = a.items[rec.y];
-                off = it.x;
-                total = is_front ? it.y : it.y + a.items2[rec.y].x;
-            }
-        }
-        float thr = __uint_as_float(rec.z);            // NaN without a reliable estimate: nothing is culled
-        // the walk below reads the lane's tile entry by entry: ask for the first lines now, the rest as the walk advances
-        if (total) {
-            prefetch_l1(a.tileLB + off);
-            for (uint32_t e = 0; e < min(total, 16u); e += 4) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + e));
-        }
-        ws.P[lane] = P;
-        ws.best[lane] = KEY_NONE;
-        __syncwarp();
-        bool cut = false;
-        uint32_t live = __ballot_sync(0xffffffffu, total > 0u);
-        for (uint32_t j = 0; live; ++j) {
-            bool hit = false;
-            if (!cut && j < total) {
-                if ((j & 3u) == 0u && j + 16u < total) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + j + 16u));
-                if ((j & 31u) == 0u && j + 32u < total) prefetch_l1(a.tileLB + off + j + 32u);
-                const float lb = a.tileLB[off + j];
-                if (lb > thr) {
-                    cut = true;                           // everything from here on is farther than the incumbent
-                } else {
-                    const float4 ca = a.tileAB[2 * static_cast<size_t>(off + j)], cb = a.tileAB[2 * static_cast<size_t>(off + j) + 1];
-                    hit = cull_pass(P.x, P.y, P.z, ca, cb, thr);
-                    ++culls;
-                }
-            }
-            push(hit, off + j);
-            if (qn >= 32u) {
-                drain();
-                thr = fminf(thr, thr_of(ws.best[lane], a.slack));     // fminf ignores a NaN operand
-            }
-            live = __ballot_sync(0xffffffffu, !cut && j + 1u < total);
-        }
-        // cylinders that cannot be bounded (non-finite / non-unit axis): evaluated for every point; cylinders spanning too
-        // many voxels to be listed: cull test; variant A: points exactly on the axis line of an axis-parallel cylinder get
-        // NaN from it (and NaN wins)
-        for (uint32_t e = 0; e < a.n_special; ++e) {
-            push(valid, static_cast<uint32_t>(a.special[e]) | Q_REC);
-            while (qn >= 32u) drain();
-        }
-        if (a.n_long) {
-            while (qn) drain();
-            thr = fminf(thr, thr_of(ws.best[lane], a.slack));
-            for (uint32_t e = 0; e < a.n_long; ++e) {
-                const uint32_t ci = static_cast<uint32_t>(a.long_list[e]);
-                const bool hit = valid && cull_pass(P.x, P.y, P.z, a.recA[ci], a.recB[ci], thr);
-                culls += valid ? 1u : 0u;
-                push(hit, ci | Q_REC);
-                while (qn >= 32u) drain();
-            }
-        }
-        if (!GUARD) {
-            for (uint32_t e = 0; e < a.n_aligned; ++e) {
-                const uint32_t ci = static_cast<uint32_t>(a.aligned[e]);
-                push(valid && on_axis_line(P.x, P.y, P.z, a.recA[ci], a.recB[ci]), ci | Q_REC);
-                while (qn >= 32u) drain();
-            }
-        }
-        while (qn) drain();
-        const unsigned long long key = ws.best[lane];
-        thr = fminf(thr, thr_of(key, a.slack));
-        // NaN incumbent (hi word 0) is final: NaN beats everything.  Near-certified: the exact distance is inside D_near.
-        // Otherwise: an entry beyond the incumbent ended the walk, or the whole tile was searched and the incumbent is
-        // inside D_max — everything else is farther.  KEY_NONE is never certified.
-        const bool nan_key = static_cast<uint32_t>(key >> 32) == 0u;
-        const bool near_ok = thr_of(key, a.slack) <= a.near;
-        const bool far_ok = !is_front && key != KEY_NONE && (cut || thr <= a.reach);
-        const bool done = valid && (nan_key || near_ok || far_ok);
-        if (done) a.win[__float_as_int(P.w)] = static_cast<int32_t>(key_index(key));
-        nfar += __popc(__ballot_sync(0xffffffffu, done && !nan_key && !near_ok));
-        const bool pend = valid && !done;
-        const uint32_t sp = warp_append(pend, &a.st->pending, lane, lt);
-        if (pend) {
-            a.pend_idx[sp] = __float_as_int(P.w);
-            a.pend_keys[sp] = key;
-        }
-        __syncwarp();                    // ws.P / ws.best are rewritten by the next round
+        if (w < w_all - w_front) exact_task<GUARD, NFMA, DIRECT, EXACT_FAR_LANES>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
+        else exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w - (w_all - w_front), true, n_front, qn, pairs, culls, nfar);
     }
     unsigned long long all_culls = culls;
 #pragma unroll
@@ -1470,10 +1503,14 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
 // ------------------------------------------------------------------------------------------------
 // host driver of the direct path
 // ------------------------------------------------------------------------------------------------
-static bool use_direct(const tm_handle *, const LabelArgs &) {
+// Small clouds take the direct path: the sorted path pays ~0.1 ms per call that does not depend on the number of points
+// (scan over every voxel of the grid, a dozen launches), the direct path pays ~0.25 us per 1000 points for its uncoalesced
+// tile reads.  Measured crossover on a randomly ordered cloud against 50k cylinders: ~800k points
+// (profiles/r02_floor_phases.json); TM_DIRECT=0/1 forces either.
+static bool use_direct(const tm_handle *, const LabelArgs &a) {
     static const int forced = [] { const char *e = getenv("TM_DIRECT"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced != 0;
-    return false;
+    return a.n <= 600000;
 }
 
 static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, float slack) {
@@ -1502,6 +1539,8 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     ev.tileLB = h->tileLB.as<float>();
     ev.atol = a.prm.perp_atol; ev.eps = a.prm.norm_eps;
     ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
+    ev.pf = 3;
+    if (const char *env = getenv("TM_PF")) ev.pf = atoi(env);
     ev.amb = slack;
     if (const char *env = getenv("TM_AMB_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v > 0.f && v <= 1.f) ev.amb = slack * v; }
     int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();
@@ -1640,6 +1679,8 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
     // allowance of the estimate-vs-reference comparison: the same rounding slack by default (TM_AMB_FACTOR scales it down
     // for experiments; never above the slack)
+    ev.pf = 3;
+    if (const char *env = getenv("TM_PF")) ev.pf = atoi(env);
     ev.amb = slack;
     if (const char *env = getenv("TM_AMB_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v > 0.f && v <= 1.f) ev.amb = slack * v; }
     int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();       // the caller's index array doubles as the scatter target
