@@ -236,13 +236,14 @@ def project_clouds(cloudList, cylinderList, labelDir, batch_size=1024, use_featu
         if align_qsm_to_cloud:
             table = _align_to_cloud(table, cloud[:, :3], cloud_path)
 
-        projected = generate_offset_cloud_cuda_batched(cloud, table, device, batch_size=batch_size)
+        os.makedirs(labelDir, exist_ok=True)
+        target = os.path.join(labelDir, cloud_stem + suffix)
         if use_features:
+            projected = generate_offset_cloud_cuda_batched(cloud, table, device, batch_size=batch_size)
             projected = add_features(projected, use_densities=False, use_curvatures=False, use_distances=False,
                                      use_verticalities=False)
-        else:
-            projected = np.concatenate([projected, np.ones((len(projected), 4), dtype=projected.dtype)], axis=1)
-        os.makedirs(labelDir, exist_ok=True)
-        np.save(os.path.join(labelDir, cloud_stem + suffix), projected)
+            np.save(target, projected)
+        else:       # the (N,11) rows (four columns of ones appended) are written once, straight into the .npy file
+            dropin.offset_cloud_to_npy(target, cloud, table, device, VARIANT)
         done += 1
     print(f"\n✅ Finished labeling and saving! {done} cloud(s) processed.")

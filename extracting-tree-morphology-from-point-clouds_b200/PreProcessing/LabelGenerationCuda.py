@@ -64,14 +64,15 @@ def label_clouds(cloudDir, cylinderDir, labelDir, batch_size=1024, clean_data=Fa
         cloud = np.load(cloud_path)
         cylinders = pd.read_csv(table_path, header=0)
         cylinders.columns = cylinders.columns.str.strip()
-        labelled = generate_offset_cloud_cuda_batched(cloud, cylinders, device, batch_size=batch_size)
+        stem = os.path.basename(cloud_path).split(".")[0]
+        target = os.path.join(labelDir, stem + "_labeled.npy")
         if use_features:
+            labelled = generate_offset_cloud_cuda_batched(cloud, cylinders, device, batch_size=batch_size)
             labelled = add_features(labelled, use_densities=False, use_curvatures=False, use_distances=False,
                                     use_verticalities=False)
-        else:       # four dummy feature columns keep the (N,11) layout TreeSet expects
-            labelled = np.concatenate([labelled, np.ones((len(labelled), 4), dtype=int)], axis=1)
-        stem = os.path.basename(cloud_path).split(".")[0]
-        np.save(os.path.join(labelDir, stem + "_labeled.npy"), labelled)
+            np.save(target, labelled)
+        else:       # four dummy feature columns keep the (N,11) layout TreeSet expects: rows written once, into the file
+            dropin.offset_cloud_to_npy(target, cloud, cylinders, device, VARIANT)
     print("Finished labeling and saving!")
 
 

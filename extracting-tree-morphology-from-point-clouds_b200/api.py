@@ -195,8 +195,11 @@ class Engine:
 
     def label_cloud_host(self, cloud: np.ndarray, variant: Variant = VARIANT_A, move_to_mantle: bool = True,
                          norm_fma: bool = False, mode: str = "auto", cell_size: float = 0.0,
-                         out: np.ndarray | None = None, want_dist: bool = False):
-        """generate_offset_cloud_cuda_batched for a host cloud: pipelined H2D / label / assemble / D2H."""
+                         out: np.ndarray | None = None, want_dist: bool = False, tail=None):
+        """generate_offset_cloud_cuda_batched for a host cloud: pipelined H2D / label / assemble / D2H.
+
+        ``tail``: values of extra columns appended to every row (the drivers' four dummy feature columns); ``out`` is then
+        ``(N, 7 + len(tail))`` and may be a memory-mapped ``.npy`` file."""
         cloud = np.asarray(cloud)
         if cloud.ndim != 2 or cloud.shape[1] < 3:
             raise ValueError(f"cloud must be (N, >=3), got {cloud.shape}")
@@ -206,32 +209,39 @@ class Engine:
                                    or cloud.strides[0] < 3 * cloud.itemsize):
             cloud = np.ascontiguousarray(cloud)
         n = cloud.shape[0]
+        width = 7 + (len(tail) if tail is not None else 0)
         if out is None:
-            out = self._new_records(n)
-        if out.shape != (n, 7) or out.dtype != np.float64 or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous float64 (N,7) array")
+            out = self._new_records(n, width)
+        if out.shape != (n, width) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float64 (N,{width}) array")
         dist = np.empty(n, dtype=np.float32) if want_dist else None
         prm = self._params(variant, move_to_mantle, norm_fma, mode, cell_size)
         row_stride = cloud.strides[0] // cloud.itemsize if n > 1 else max(3, cloud.shape[1])
-        self._check(self._lib.tm_label_cloud_host(
-            self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride,
-            ctypes.byref(prm), out.ctypes.data, dist.ctypes.data if dist is not None else None))
+        if width == 7:
+            self._check(self._lib.tm_label_cloud_host(
+                self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride,
+                ctypes.byref(prm), out.ctypes.data, dist.ctypes.data if dist is not None else None))
+        else:
+            tl = (ctypes.c_double * (width - 7))(*[float(v) for v in tail])
+            self._check(self._lib.tm_label_cloud_host_wide(
+                self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride,
+                ctypes.byref(prm), out.ctypes.data, width, tl, dist.ctypes.data if dist is not None else None))
         return (out, dist) if want_dist else out
 
     @staticmethod
-    def _new_records(n: int) -> np.ndarray:
+    def _new_records(n: int, width: int = 7) -> np.ndarray:
         """The (N,7) float64 result array.  Page-locked by default (torch's caching host allocator, so repeated calls reuse
         the block): a fresh pageable array costs more in first-touch page faults than the labelling itself (10M points:
         27 ms pageable, 16 ms page-locked, profiles/r01i_host_pipeline.md).  Bounded: arrays above TM_PINNED_OUT_MAX_MB
         (default 4096) or beyond TM_PINNED_OUT_TOTAL_MB of live results (default 8192) are ordinary np.empty arrays, as is
         everything with TM_PINNED_OUT=0."""
         global _pinned_live
-        nbytes = n * 56
+        nbytes = n * 8 * width
         if (n > 0 and os.environ.get("TM_PINNED_OUT", "1") != "0"
                 and nbytes <= int(os.environ.get("TM_PINNED_OUT_MAX_MB", "4096")) << 20
                 and _pinned_live + nbytes <= int(os.environ.get("TM_PINNED_OUT_TOTAL_MB", "8192")) << 20):
             try:
-                t = torch.empty((n, 7), dtype=torch.float64, pin_memory=True)
+                t = torch.empty((n, width), dtype=torch.float64, pin_memory=True)
             except RuntimeError:
                 t = None
             if t is not None:
@@ -239,7 +249,7 @@ class Engine:
                 _pinned_live += nbytes
                 weakref.finalize(out.base, _pinned_released, nbytes)      # the tensor object numpy keeps as the array's base
                 return out
-        return np.empty((n, 7), dtype=np.float64)
+        return np.empty((n, width), dtype=np.float64)
 
     # -- small-table fast path (QSMFittingDepthFirst.py:1006-1094) ---------------------------------
     def upload_cloud(self, cloud: np.ndarray) -> None:

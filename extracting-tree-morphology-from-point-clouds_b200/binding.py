@@ -55,6 +55,8 @@ SIGNATURES = {
                                        c_vp, c_vp]),
     "tm_assemble_records": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "tm_label_cloud_host": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64, ctypes.POINTER(TmParams), c_vp, c_vp]),
+    "tm_label_cloud_host_wide": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64, ctypes.POINTER(TmParams), c_vp, c_i32,
+                                                ctypes.POINTER(ctypes.c_double), c_vp]),
     "tm_cloud_upload_host": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64]),
     "tm_proximity_flags_host": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, ctypes.POINTER(TmParams), c_f32,
                                                c_f32, c_vp, c_vp, c_vp]),

@@ -521,13 +521,14 @@ static inline void store_f64(double *dst, double v) {
 }
 
 template <typename T>
-static void assemble_rows_host(const T *cloud, int64_t row_stride, const float4 *packed, double *out, int64_t r0, int64_t r1) {
+static void assemble_rows_host(const T *cloud, int64_t row_stride, const float4 *packed, double *out, int64_t r0, int64_t r1,
+                               int32_t width, const double *tail) {
     for (int64_t r = r0; r < r1; ++r) {
         const T *p = cloud + r * row_stride;
         const float4 k = packed[r];
         int32_t id;
         memcpy(&id, &k.w, 4);
-        double *o = out + 7 * r;
+        double *o = out + static_cast<int64_t>(width) * r;
         store_f64(o + 0, static_cast<double>(p[0]));
         store_f64(o + 1, static_cast<double>(p[1]));
         store_f64(o + 2, static_cast<double>(p[2]));
@@ -535,6 +536,7 @@ static void assemble_rows_host(const T *cloud, int64_t row_stride, const float4 
         store_f64(o + 4, static_cast<double>(k.y));
         store_f64(o + 5, static_cast<double>(k.z));
         store_f64(o + 6, static_cast<double>(id));
+        for (int32_t c = 7; c < width; ++c) store_f64(o + c, tail[c - 7]);       // the drivers' feature columns (ones)
     }
 #if defined(__x86_64__)
     _mm_sfence();
@@ -558,7 +560,8 @@ static void stage_rows_f32(const T *cloud, int64_t row_stride, float *dst, int64
 // host workers assemble earlier chunks' records.  Up to PIPE_SLOTS chunks are in flight; a chunk's buffers are reused
 // only after the chunk has been assembled (hence fully transferred).
 static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride,
-                                     const tm_params *params, double *out_records_host, float *out_dist_host, unsigned nthreads) {
+                                     const tm_params *params, double *out_records_host, float *out_dist_host, unsigned nthreads,
+                                     int32_t width = 7, const double *tail = nullptr) {
     if (!h->pool || h->pool->n != nthreads) {
         delete h->pool;
         h->pool = new (std::nothrow) tmn::HostPool(nthreads);
@@ -583,7 +586,7 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     // workers assemble the others (16 B/point + the host's stores).  See profiles/r01i_host_pipeline.md.  (float32 clouds
     // only: the device sees the float32 rounding of a float64 cloud, the records carry the caller's own values.)
     int split = 0;
-    if (const char *env = getenv("TM_HOST_SPLIT")) { if (dtype == TM_F32 && host_is_pinned(out_records_host)) split = std::max(0, std::min(100, atoi(env))); }
+    if (const char *env = getenv("TM_HOST_SPLIT")) { if (width == 7 && dtype == TM_F32 && host_is_pinned(out_records_host)) split = std::max(0, std::min(100, atoi(env))); }
     auto on_device = [split](int64_t c) { return ((c + 1) * split) / 100 > (c * split) / 100; };
     for (int b = 0; b < depth; ++b) {
         if (!direct_in) TM_CUDA(h, h->pinned_in[b].ensure(in_bytes));
@@ -679,11 +682,13 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
         if (!on_device(c)) {
             const float4 *packed = static_cast<const float4 *>(h->pinned_out[b].p);
             const unsigned char *crow = src + static_cast<size_t>(c) * static_cast<size_t>(chunk) * static_cast<size_t>(row_stride) * esz;
-            double *orow = out_records_host + c * chunk * 7;
+            double *orow = out_records_host + c * chunk * width;
+            double tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int32_t k = 7; k < width; ++k) tl[k - 7] = tail[k - 7];
             h->pool->run([=](unsigned t, unsigned nt) {
                 const int64_t per = (cnt + nt - 1) / nt, r0 = std::min<int64_t>(cnt, t * per), r1 = std::min<int64_t>(cnt, r0 + per);
-                if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1);
-                else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1);
+                if (dtype == TM_F32) assemble_rows_host(reinterpret_cast<const float *>(crow), row_stride, packed, orow, r0, r1, width, tl);
+                else assemble_rows_host(reinterpret_cast<const double *>(crow), row_stride, packed, orow, r0, r1, width, tl);
             });
         }
         if (out_dist_host)
@@ -868,6 +873,29 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t dtype, int
     h->stats.pairs_evaluated = total.pairs_evaluated;
     h->stats.points_brute = total.points_brute;
     return TM_OK;
+}
+
+int tm_label_cloud_host_wide(tm_handle *h, const void *cloud_host, int32_t dtype, int64_t n, int64_t row_stride,
+                             const tm_params *params, double *out_rows_host, int32_t row_doubles, const double *tail_values,
+                             float *out_dist_host) {
+    if (!h) return TM_ERR_INVALID;
+    if (row_doubles == 7) return tm_label_cloud_host(h, cloud_host, dtype, n, row_stride, params, out_rows_host, out_dist_host);
+    int rc = check_params(h, params);
+    if (rc != TM_OK) return rc;
+    if (n < 0) return fail(h, TM_ERR_INVALID, "tm_label_cloud_host_wide: negative point count%s%s");
+    if (n == 0) return TM_OK;
+    if (!cloud_host || !out_rows_host || row_stride < 3 || (dtype != TM_F32 && dtype != TM_F64) || row_doubles < 7 ||
+        row_doubles > 15 || !tail_values)
+        return fail(h, TM_ERR_INVALID, "tm_label_cloud_host_wide: bad argument%s%s");
+    if (!h->have_cyl) return fail(h, TM_ERR_STATE, "tm_label_cloud_host_wide called before tm_set_cylinders%s%s");
+    if (h->m == 0) return fail(h, TM_ERR_NO_CYLINDERS, "%s%s", tm_status_string(TM_ERR_NO_CYLINDERS));
+    TM_CUDA(h, cudaSetDevice(h->device));
+    for (auto &s : h->pipe_stream) if (!s) TM_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto &e : h->pipe_event) if (!e) TM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // the wide rows are always written by the host workers (the device never sees the feature columns)
+    const unsigned ht = std::max(1u, std::min(host_threads_available(), 16u));
+    return label_cloud_host_assemble(h, cloud_host, dtype, n, row_stride, params, out_rows_host, out_dist_host, ht, row_doubles,
+                                     tail_values);
 }
 
 // ---- small-table fast path ------------------------------------------------------------------------

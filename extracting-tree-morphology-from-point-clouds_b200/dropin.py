@@ -6,6 +6,8 @@ parameterised by ``api.Variant`` and both modules forward to it.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -78,7 +80,7 @@ def closest_cylinder(points, start, radius, axis_length, axis_unit, IDs, device,
     return res["id"].cpu().numpy(), res["dist"].cpu().numpy(), res["offset"].cpu().numpy()
 
 
-def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None, batch_size=1024):
+def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None, batch_size=1024, out=None, tail=None):
     """``generate_offset_cloud_cuda_batched`` (LabelGenerationCuda.py:113-135 / Projection.py:117-144).
 
     cloud: (N, >=3) array; cylinders: DataFrame with the QSM columns.  Returns float64 (N,7)
@@ -112,5 +114,49 @@ def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None,
     if cloud.ndim != 2 or cloud.shape[1] < 3:
         raise ValueError(f"cloud must have shape (N, >=3), got {cloud.shape}")
     if len(cloud) == 0:
-        return np.zeros((0, 7))
-    return eng.label_cloud_host(cloud, variant, norm_fma=norm_fma)
+        return np.zeros((0, 7 + (len(tail) if tail is not None else 0)))
+    return eng.label_cloud_host(cloud, variant, norm_fma=norm_fma, out=out, tail=tail)
+
+
+def offset_cloud_to_npy(path, cloud, cylinders, device, variant: api.Variant, tail=(1.0, 1.0, 1.0, 1.0)):
+    """``np.save(path, np.concatenate([generate_offset_cloud_cuda_batched(...), ones((N,4))], axis=1))`` in one pass
+    (LabelGenerationCuda.py:196-205, Projection.py:416-438 without features): the host workers of the library write the
+    (N,11) rows once, into a page-locked array that is reused from call to call (no first-touch page faults, no
+    ``np.concatenate`` copy), and the file is written from it by a few threads with ``pwrite`` — the same bytes ``np.save``
+    produces (format 1.0 header, C-ordered little-endian float64)."""
+    n = len(cloud)
+    width = 7 + len(tail)
+    if n == 0:
+        np.save(path, np.zeros((0, width)))
+        return
+    rows = api.Engine._new_records(n, width)
+    offset_cloud(cloud, cylinders, device, variant, out=rows, tail=tail)
+    _write_npy(path, rows)
+
+
+def _write_npy(path, array: np.ndarray, threads: int = 4) -> None:
+    """np.save for a C-contiguous array, with the payload copied into the page cache by several threads."""
+    import io
+    from concurrent.futures import ThreadPoolExecutor
+    head = io.BytesIO()
+    np.lib.format.write_array_header_1_0(head, np.lib.format.header_data_from_array_1_0(array))
+    header = head.getvalue()
+    payload = memoryview(array).cast("B")
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
+    try:
+        os.write(fd, header)
+        size = len(payload)
+        step = max(8 << 20, -(-size // threads))
+        spans = [(lo, min(size, lo + step)) for lo in range(0, size, step)]
+
+        def put(span):
+            lo, hi = span
+            while lo < hi:
+                lo += os.pwrite(fd, payload[lo:hi], len(header) + lo)
+        if len(spans) > 1:
+            with ThreadPoolExecutor(len(spans)) as pool:
+                list(pool.map(put, spans))
+        else:
+            put(spans[0])
+    finally:
+        os.close(fd)

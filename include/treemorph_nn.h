@@ -174,6 +174,18 @@ int tm_label_cloud_host(tm_handle *h, const void *cloud_host, int32_t cloud_dtyp
                         double *out_records_host, float *out_dist_host);
 
 /*
+ * The same call writing the drivers' final record directly: rows of `row_doubles` (7..15) float64, the first seven as above,
+ * the others filled with tail_values[0 .. row_doubles-7) — label_clouds / project_clouds without features append four
+ * columns of ones to get the (N,11) layout TreeSet expects (LabelGenerationCuda.py:199-200, Projection.py:428-432).
+ * out_rows_host may be a memory-mapped .npy file: the rows are written once, with streaming stores, where np.save would
+ * otherwise copy them a second time (LabelGenerationCuda.py:203-205).  row_doubles == 7 is tm_label_cloud_host.
+ */
+int tm_label_cloud_host_wide(tm_handle *h, const void *cloud_host, int32_t cloud_dtype, int64_t n,
+                             int64_t cloud_row_stride, const tm_params *params,
+                             double *out_rows_host, int32_t row_doubles, const double *tail_values,
+                             float *out_dist_host);
+
+/*
  * Small-table fast path — the call pattern of cylinder_proximity_based_segmentation
  * (Modules/Pipeline/QSMFittingDepthFirst.py:1006-1094): thousands of calls per tree, each against the few
  * cylinders fitted last and a subset of the SAME cloud, keeping one bit per point (:1084).
