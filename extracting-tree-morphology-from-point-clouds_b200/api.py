@@ -137,6 +137,58 @@ class Engine:
         self.m = m
         self.installs += 1
 
+    # -- multi-GPU: communicator + table broadcast through the C ABI (NCCL bound by the library) ---------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId (128 bytes) — rank 0 makes it and ships it to the other ranks."""
+        lib = B.load()
+        buf = ctypes.create_string_buffer(B.TM_COMM_ID_BYTES)
+        B.check(lib, None, lib.tm_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, unique_id: bytes, nranks: int, rank: int) -> None:
+        if len(unique_id) != B.TM_COMM_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        self._check(self._lib.tm_comm_init_rank(self._h, unique_id, int(nranks), int(rank)))
+
+    def comm_destroy(self) -> None:
+        self._check(self._lib.tm_comm_destroy(self._h))
+
+    def comm_info(self) -> tuple[int, int]:
+        r, n = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self._lib.tm_comm_info(self._h, ctypes.byref(r), ctypes.byref(n)))
+        return int(r.value), int(n.value)
+
+    def broadcast_cylinders(self, start=None, radius=None, axis_length=None, axis_unit=None, ids=None, root: int = 0) -> int:
+        """Replicate the root's cylinder table on every rank of the communicator and install it (tm_broadcast_cylinders).
+        The arguments are read on ``root`` only.  Returns M."""
+        rank, size = self.comm_info()
+        if rank == root or size == 1:
+            start = self._f32(start, 3)
+            unit = self._f32(axis_unit, 3)
+            m = start.shape[0]
+            length = self._f32(axis_length).reshape(-1)
+            radius = self._f32(radius).reshape(-1)
+            if ids is not None:
+                ids = torch.as_tensor(ids)
+                if ids.device != self.device or ids.dtype != torch.int32:
+                    ids = ids.to(device=self.device, dtype=torch.int32)
+                ids = ids.reshape(-1)
+            args = (_ptr(start), start.stride(0), start.stride(1), _ptr(unit), unit.stride(0), unit.stride(1),
+                    _ptr(length), length.stride(0) if m else 1, _ptr(radius), radius.stride(0) if m else 1,
+                    _ptr(ids), (ids.stride(0) if m else 1) if ids is not None else 1, m)
+        else:
+            args = (None, 3, 1, None, 3, 1, None, 1, None, 1, None, 1, 0)
+        self._check(self._lib.tm_broadcast_cylinders(self._h, *args, int(root), _stream_ptr(self.device)))
+        self.installs += 1
+        self.m = int(self.stats_m())
+        return self.m
+
+    def stats_m(self) -> int:
+        m = ctypes.c_int64()
+        self._check(self._lib.tm_cylinder_count(self._h, ctypes.byref(m)))
+        return int(m.value)
+
     # -- point side --------------------------------------------------------------------------
     def _params(self, variant: Variant, move_to_mantle: bool, norm_fma: bool, mode: str, cell_size: float) -> B.TmParams:
         p = B.TmParams()

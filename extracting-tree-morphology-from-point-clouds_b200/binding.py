@@ -13,8 +13,9 @@ from . import build as _build
 TM_OK, TM_ERR_INVALID, TM_ERR_NO_CYLINDERS, TM_ERR_CUDA, TM_ERR_NOMEM, TM_ERR_STATE = range(6)
 TM_MODE_AUTO, TM_MODE_BRUTE, TM_MODE_GRID = 0, 1, 2
 TM_F32, TM_F64 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 TM_PHASES = 9
+TM_COMM_ID_BYTES = 128
 PHASE_NAMES = ("bin", "scan", "scatter", "evaluate", "tree", "exhaustive", "pending", "epilogue", "total")
 
 c_i64, c_i32, c_f32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
@@ -51,6 +52,16 @@ SIGNATURES = {
                                             c_vp, c_vp, c_vp]),
     "tm_set_cylinders": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
                                         c_vp, c_i64, c_i64, c_vp]),
+    "tm_cylinder_count": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i64)]),
+    "tm_comm_unique_id": (ctypes.c_int, [c_vp]),
+    "tm_comm_init_rank": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32]),
+    "tm_comm_init_all": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32]),
+    "tm_comm_destroy": (ctypes.c_int, [c_vp]),
+    "tm_comm_info": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
+    "tm_broadcast_cylinders": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64,
+                                              c_vp, c_i64, c_i64, c_i32, c_vp]),
+    "tm_broadcast_cylinders_all": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, c_i64,
+                                                  c_vp, c_i64, c_vp, c_i64, c_i64, c_i32]),
     "tm_label_points": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.POINTER(TmParams), c_vp, c_vp, c_vp, c_vp,
                                        c_vp, c_vp]),
     "tm_assemble_records": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),

@@ -17,10 +17,10 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtreemorph_nn.so")
-SOURCES = ["tm_api.cu", "tm_brute.cu", "tm_grid.cu", "tm_small.cu", "tm_bvh.cu", "tm_knn.cu", "tm_noise.cu"]
+SOURCES = ["tm_api.cu", "tm_brute.cu", "tm_grid.cu", "tm_small.cu", "tm_bvh.cu", "tm_knn.cu", "tm_noise.cu", "tm_comm.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "--threads", "6"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "--threads", "8", "-ldl"]
 
 
 def find_nvcc() -> str | None:

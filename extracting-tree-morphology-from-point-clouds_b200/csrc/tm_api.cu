@@ -314,6 +314,9 @@ int tm_destroy(tm_handle *h) {
                           &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileAB, &h->tileI, &h->items, &h->items2, &h->warp_item, &h->undecided, &h->late_rows, &h->tile_desc,
                           &h->pend_idx, &h->brute_slots, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
                           &h->small_out, &h->bvh_scratch};
+    tm_comm_destroy(h);
+    h->comm_table.release();
+    h->comm_count.release();
     for (auto *b : bufs) b->release();
     for (int i = 0; i < tmn::PIPE_SLOTS; ++i) {
         h->chunk_in[i].release(); h->chunk_rec[i].release(); h->chunk_off[i].release(); h->chunk_id[i].release();

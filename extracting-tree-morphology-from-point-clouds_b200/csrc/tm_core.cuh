@@ -174,6 +174,11 @@ struct tm_handle {
     // ---- point features (tm_knn.cu) ----
     tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box;
 
+    // ---- multi-GPU (tm_comm.cu) ----
+    void *comm = nullptr;            // ncclComm_t
+    int32_t comm_rank = 0, comm_size = 0;
+    tmn::DevBuf comm_table, comm_count;      // packed (M,9) table as broadcast, its row count
+
     // ---- optional phase timing ----
     bool profiling = false;
     cudaEvent_t phase_ev[TM_PHASES + 1] = {nullptr};

@@ -65,6 +65,18 @@ def broadcast_table(table: torch.Tensor | None, device, src: int = 0) -> torch.T
     return buf
 
 
+def init_engine_comm(engine) -> None:
+    """Give `engine` its own NCCL communicator through the C ABI (tm_comm_init_rank): rank 0 makes the unique id, torch's
+    process group only ships its 128 bytes.  After this ``engine.broadcast_cylinders`` replicates and installs a table
+    without torch.distributed on the path."""
+    rank, size = world()
+    if size == 1:
+        return
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    engine.comm_init_rank(box[0], size, rank)
+
+
 def label_sharded(label_fn, cloud: np.ndarray | None, table: torch.Tensor | None, device, src: int = 0):
     """Label an n-point host cloud held by `src` across all ranks.
 

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define TM_ABI_VERSION 6
+#define TM_ABI_VERSION 7
 
 /* status codes */
 #define TM_OK               0
@@ -140,6 +140,42 @@ int tm_set_cylinders(tm_handle *h,
                      const float *radius, int64_t radius_stride,
                      const int32_t *ids, int64_t ids_stride,
                      int64_t m, void *stream);
+
+/*
+ * Multi-GPU: the search shards by POINTS, every rank needs the whole cylinder table and nothing else, so the
+ * only collective is one broadcast of the table from the rank that read the QSM (the tensors built at
+ * LabelGenerationCuda.py:117-123 / Projection.py:121-132); afterwards each rank labels its own rows with tm_label_points /
+ * tm_label_cloud_host and no data-path collective follows.  NCCL is bound at run time (dlopen of libnccl.so.2).
+ *
+ *   one process per GPU:   rank 0 calls tm_comm_unique_id and ships the 128 bytes to the others (MPI, a file, torch's store);
+ *                          every rank calls tm_comm_init_rank on its own handle, then tm_broadcast_cylinders (the cylinder
+ *                          pointers / m are read on `root` only; strides in elements as for tm_set_cylinders).  On return the
+ *                          table is installed on every rank, exactly as tm_set_cylinders would have installed it.
+ *   one process, N GPUs:   tm_comm_init_all over N handles (one per device), tm_broadcast_cylinders_all with the source
+ *                          pointers on handles[root_index]'s device.
+ * Without a communicator (or with one rank) tm_broadcast_cylinders is tm_set_cylinders.  Both synchronise.
+ */
+#define TM_COMM_ID_BYTES 128
+int tm_cylinder_count(const tm_handle *h, int64_t *m);           /* rows of the installed table */
+int tm_comm_unique_id(void *id_out);
+int tm_comm_init_rank(tm_handle *h, const void *id, int32_t nranks, int32_t rank);
+int tm_comm_init_all(tm_handle **handles, int32_t ndev);
+int tm_comm_destroy(tm_handle *h);
+int tm_comm_info(const tm_handle *h, int32_t *rank, int32_t *nranks);
+int tm_broadcast_cylinders(tm_handle *h,
+                           const float *start, int64_t start_row_stride, int64_t start_col_stride,
+                           const float *axis_unit, int64_t unit_row_stride, int64_t unit_col_stride,
+                           const float *axis_length, int64_t length_stride,
+                           const float *radius, int64_t radius_stride,
+                           const int32_t *ids, int64_t ids_stride,
+                           int64_t m, int32_t root, void *stream);
+int tm_broadcast_cylinders_all(tm_handle **handles, int32_t ndev,
+                               const float *start, int64_t start_row_stride, int64_t start_col_stride,
+                               const float *axis_unit, int64_t unit_row_stride, int64_t unit_col_stride,
+                               const float *axis_length, int64_t length_stride,
+                               const float *radius, int64_t radius_stride,
+                               const int32_t *ids, int64_t ids_stride,
+                               int64_t m, int32_t root_index);
 
 /*
  * closest_cylinder_cuda_batch for N device-resident points (LabelGenerationCuda.py:20-111,

@@ -61,3 +61,65 @@ def test_two_gpu_sharded_labelling_matches_single_gpu(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok.npy")
+
+
+def _cabi_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), LOCAL_WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # only ships the 128-byte NCCL id
+    try:
+        from treemorph_b200 import api, sharding, synth
+        from oracle import oracle
+        eng = api.Engine(dev)
+        sharding.init_engine_comm(eng)
+        assert eng.comm_info() == (rank, world)
+        q = synth.random_qsm(3000, seed=41, id_offset=7)
+        pts = synth.sample_points(q, 50_000, seed=42)
+        if rank == 0:                              # only the root holds the table
+            start, radius, length, unit, ids = synth.cylinder_arrays(q)
+            m = eng.broadcast_cylinders(torch.tensor(start, device=dev), torch.tensor(radius, device=dev), torch.tensor(length, device=dev),
+                                        torch.tensor(unit, device=dev), torch.tensor(ids, device=dev), root=0)
+        else:
+            m = eng.broadcast_cylinders(root=0)
+        assert m == 3000
+        lo, hi = sharding.shard_bounds(len(pts), world, rank)
+        got = eng.label(torch.tensor(pts[lo:hi], device=dev), api.VARIANT_A, mode="grid")
+        start, radius, length, unit, ids = synth.cylinder_arrays(q)
+        want = oracle.label(pts[lo:hi], start, radius, length, unit, ids, oracle.VARIANT_A)
+        assert (got["id"].cpu().numpy() == want["id"]).all() and np.array_equal(got["dist"].cpu().numpy(), want["dist"], equal_nan=True)
+        assert np.array_equal(got["offset"].cpu().numpy(), want["offset"], equal_nan=True)
+        eng.comm_destroy()
+        eng.close()
+        np.save(os.path.join(tmpdir, f"ok{rank}.npy"), np.array([1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_c_abi_communicator_broadcasts_and_installs_the_table(tmp_path):
+    """tm_comm_unique_id / tm_comm_init_rank / tm_broadcast_cylinders: rank 1 never sees the QSM, labels its rows against
+    the table NCCL delivered, and matches the oracle bit for bit."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_cabi_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0.npy") and os.path.exists(tmp_path / "ok1.npy")
+
+
+def test_broadcast_without_a_communicator_is_an_install():
+    from treemorph_b200 import api, synth
+    from oracle import oracle
+    dev = torch.device("cuda", 0)
+    eng = api.Engine(dev)
+    q = synth.random_qsm(500, seed=43)
+    start, radius, length, unit, ids = synth.cylinder_arrays(q)
+    assert eng.comm_info() == (0, 1)
+    assert eng.broadcast_cylinders(torch.tensor(start, device=dev), torch.tensor(radius, device=dev), torch.tensor(length, device=dev),
+                                   torch.tensor(unit, device=dev), torch.tensor(ids, device=dev)) == 500
+    pts = synth.sample_points(q, 5000, seed=44)
+    got = eng.label(torch.tensor(pts, device=dev), api.VARIANT_A)
+    want = oracle.label(pts, start, radius, length, unit, ids, oracle.VARIANT_A)
+    assert (got["id"].cpu().numpy() == want["id"]).all()
+    eng.close()
