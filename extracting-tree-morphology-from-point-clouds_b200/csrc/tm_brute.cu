@@ -258,9 +258,12 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
     int P, splits;
     int64_t nblk;
     {
-        // points per thread: 2 once there are enough points to fill the machine twice over
+        // points per thread: 2 once there are enough points to fill the machine (the two 128-bit broadcast loads of a
+        // cylinder then serve two evaluations: 0.60 -> 0.69 of the FP32 issue roofline, profiles/r02_brute_kernel.md;
+        // 4 points per thread measured within noise of 2: TM_BRUTE_P selects it for experiments)
         const int64_t full_wave = static_cast<int64_t>(h->sm_count) * 3 * BRUTE_THREADS;
-        P = (n_launch >= 4 * full_wave) ? 2 : 1;
+        P = (n_launch >= 2 * full_wave) ? 2 : 1;
+        if (const char *env = getenv("TM_BRUTE_P")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) P = v; }
         nblk = (n_launch + BRUTE_THREADS * P - 1) / (BRUTE_THREADS * P);
         const int64_t want_ctas = static_cast<int64_t>(h->sm_count) * 6;
         splits = 1;
@@ -279,7 +282,10 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
 #define TM_BRUTE_CASE(PP, G, F)                                                                                   \
     e = launch_brute<PP, G, F>(grid, a.stream, a.pts, n_launch, a.row_stride, sel, d_count, A, B, m, tps,           \
                                a.prm.perp_atol, a.prm.norm_eps, keys, use_atomic)
-    if (P == 2) {
+    if (P == 4) {
+        if (guard) { if (nfma) TM_BRUTE_CASE(4, true, true); else TM_BRUTE_CASE(4, true, false); }
+        else       { if (nfma) TM_BRUTE_CASE(4, false, true); else TM_BRUTE_CASE(4, false, false); }
+    } else if (P == 2) {
         if (guard) { if (nfma) TM_BRUTE_CASE(2, true, true); else TM_BRUTE_CASE(2, true, false); }
         else       { if (nfma) TM_BRUTE_CASE(2, false, true); else TM_BRUTE_CASE(2, false, false); }
     } else {
