@@ -7,6 +7,10 @@
 `launches`: per-kernel launch count / total / mean device time and SHARE of the captured launches
             (ncu --metrics gpu__time_duration.sum; cold-cache, serialised: shares are meaningful, absolutes are not).
 `kernel`:   the headline counters of one `ncu --set full` capture (needs `ncu` on PATH to read the .ncu-rep).
+`traffic`:  DRAM bytes (read + written) per launch of every per-call kernel, grouped by the phases bench.py reports, as JSON
+            (bench.py reads the newest profiles/*_dram_traffic.json for `roofline.traffic`):
+                python profiles/summarise.py traffic gpurun_out/r02_step.ncu-rep profiles/r02_dram_traffic.json <git hash>
+            The LAST launch of each kernel in the capture is used (the steady-state step of the default workload).
 """
 from __future__ import annotations
 
@@ -71,6 +75,41 @@ def launches(src: str, dst: str) -> None:
     print(open(dst).read())
 
 
+PHASE_OF = {"bin_count_kernel": "bin", "scan_reduce_kernel": "scan", "scan_blocks_kernel": "scan", "scan_apply_kernel": "scan",
+            "bin_scatter_kernel": "scatter", "evaluate_kernel": "evaluate", "exact_kernel": "evaluate", "direct_kernel": "evaluate",
+            "ring_kernel": "tree", "bvh_kernel": "tree", "brute_cull_kernel": "exhaustive", "pending_winner_kernel": "pending",
+            "finalize_rows_kernel": "epilogue"}
+
+
+def traffic(src: str, dst: str, git: str) -> None:
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    header, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(header)}
+
+    def num(row, name):
+        v = float(row[col[name]].replace(",", ""))
+        u = units[col[name]]
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6,
+                    "nsecond": 1e-3, "usecond": 1, "msecond": 1e3, "second": 1e6}.get(u, 1)
+    last = OrderedDict()
+    for row in rows[2:]:
+        last[short(row[col["Kernel Name"]])] = row
+    kernels, per_kernel = {}, {}
+    for name, row in last.items():
+        phase = PHASE_OF.get(name)
+        if phase is None:
+            continue
+        b = num(row, "dram__bytes_read.sum") + num(row, "dram__bytes_write.sum")
+        kernels[phase] = kernels.get(phase, 0.0) + b
+        per_kernel[name] = {"dram_bytes": b, "us": num(row, "gpu__time_duration.sum")}
+    with open(dst, "w") as f:
+        json.dump({"git": git, "capture": src, "workload": "bench.py default: 10M points x 50k cylinders, variant A, one B200",
+                   "kernels": kernels, "per_kernel": per_kernel}, f, indent=1)
+    print(open(dst).read())
+
+
 def kernel(src: str, dst: str) -> None:
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -96,4 +135,7 @@ def kernel(src: str, dst: str) -> None:
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
