@@ -11,13 +11,18 @@ per 1024 selected points, five small H2D copies, ~70 ATen launches and three syn
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
 from ... import api
 from ..Projection import closest_cylinder_cuda_batch  # noqa: F401  (re-exported like the reference's import, :9)
 
-_resident: dict[int, tuple] = {}            # device index -> identity of the resident cloud
+# device index -> (weak reference to the resident array, its layout, a checksum of sampled rows).  The array itself
+# decides (the weak reference dies with it: a recycled id() or address can never match), and the sampled rows catch in-place
+# edits cheaply; invalidate_resident_cloud() remains for callers that edit rows the sample does not cover.
+_resident: dict[int, tuple] = {}
 
 
 def _cuda_device(device) -> torch.device:
@@ -30,12 +35,27 @@ def _cuda_device(device) -> torch.device:
     return dev
 
 
+def _fingerprint(points: np.ndarray) -> bytes:
+    n = len(points)
+    rows = np.unique(np.linspace(0, max(n - 1, 0), num=min(n, 64)).astype(np.int64)) if n else np.zeros(0, np.int64)
+    return np.ascontiguousarray(points[rows, :3]).tobytes()
+
+
 def _ensure_resident(eng: api.Engine, dev: torch.device, points: np.ndarray) -> None:
-    iface = points.__array_interface__
-    key = (id(points), iface["data"][0], points.shape, points.strides, points.dtype.str)
-    if _resident.get(dev.index) != key:
-        eng.upload_cloud(points[:, :3])
-        _resident[dev.index] = key
+    layout = (points.__array_interface__["data"][0], points.shape, points.strides, points.dtype.str, eng.installs_cloud)
+    held = _resident.get(dev.index)
+    if held is not None:
+        ref, held_layout, held_print = held
+        if ref() is points and held_layout == layout and held_print == _fingerprint(points):
+            return
+    eng.upload_cloud(points[:, :3])
+    layout = layout[:-1] + (eng.installs_cloud,)
+    try:
+        ref = weakref.ref(points)
+    except TypeError:                       # objects that cannot be weakly referenced are uploaded every time
+        _resident.pop(dev.index, None)
+        return
+    _resident[dev.index] = (ref, layout, _fingerprint(points))
 
 
 def invalidate_resident_cloud(device=None) -> None:
@@ -78,8 +98,20 @@ def cylinder_proximity_based_segmentation(points, input_unsegmented_mask, query_
     _ensure_resident(eng, dev, points)
     # reference :1079-1084: Projection.closest_cylinder_cuda_batch (variant B) on C-contiguous tensors, unguarded
     # axis_unit (:1045); distances_batch < eps
-    flags = eng.proximity_flags(subset_indices, start_arr.astype(np.float32), end_arr.astype(np.float32),
-                                radius_arr.astype(np.float32), eps, api.VARIANT_B, axis_eps=0.0, norm_fma=True)
+    if len(start_arr) <= api.SMALL_TABLE_MAX:
+        flags = eng.proximity_flags(subset_indices, start_arr.astype(np.float32), end_arr.astype(np.float32),
+                                    radius_arr.astype(np.float32), eps, api.VARIANT_B, axis_eps=0.0, norm_fma=True)
+    else:
+        # more cylinders than the one-launch kernel holds (the reference accepts any list): the general path — prepare and
+        # install the table, label the selected rows, compare the distances with eps (reference :1084)
+        s_t = torch.as_tensor(start_arr.astype(np.float32), device=dev)
+        e_t = torch.as_tensor(end_arr.astype(np.float32), device=dev)
+        unguarded = api.Variant("B-unguarded-axis", api.VARIANT_B.perp_atol, api.VARIANT_B.norm_eps, 0.0)
+        length, unit = eng.prepare(s_t, e_t, unguarded, norm_fma=True)
+        eng.set_cylinders(s_t, torch.as_tensor(radius_arr.astype(np.float32), device=dev), length, unit, None)
+        sel = torch.as_tensor(np.ascontiguousarray(points[subset_indices, :3], dtype=np.float32), device=dev)
+        dist = eng.label(sel, api.VARIANT_B, norm_fma=True, want=("dist",))["dist"].cpu().numpy()
+        flags = dist < np.float32(eps)
     output_mask = input_unsegmented_mask.copy()
     output_mask[subset_indices[flags]] = False
     return output_mask

@@ -36,6 +36,7 @@ class Variant:
 VARIANT_A = Variant("A", 1e-6, 0.0, 0.0)       # PreProcessing/LabelGenerationCuda.py
 VARIANT_B = Variant("B", 1e-3, 1e-8, 1e-8)     # Modules/Projection.py
 VARIANTS = {"A": VARIANT_A, "B": VARIANT_B}
+SMALL_TABLE_MAX = 3072      # cylinders per tm_proximity_flags_host call (csrc/tm_core.cuh: SMALL_MAX_M)
 MODES = {"auto": B.TM_MODE_AUTO, "brute": B.TM_MODE_BRUTE, "grid": B.TM_MODE_GRID}
 
 
@@ -77,6 +78,7 @@ class Engine:
         self._h = h
         self.m = 0
         self.installs = 0          # bumped by every set_cylinders: callers that cache "my table is installed" compare it
+        self.installs_cloud = 0    # bumped by every upload_cloud: callers that cache "my cloud is resident" compare it
 
     # -- lifetime ----------------------------------------------------------------------------
     def close(self) -> None:
@@ -319,6 +321,7 @@ class Engine:
         self._check(self._lib.tm_cloud_upload_host(
             self._h, cloud.ctypes.data, B.TM_F32 if cloud.dtype == np.float32 else B.TM_F64, n, row_stride))
         self._resident_n = n
+        self.installs_cloud += 1
 
     def proximity_flags(self, subset, start, end, radius, eps: float, variant: Variant = VARIANT_B,
                         axis_eps: float = 0.0, norm_fma: bool = True, want_dist: bool = False, want_index: bool = False):

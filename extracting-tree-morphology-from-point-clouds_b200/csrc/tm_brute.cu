@@ -306,6 +306,7 @@ static int run_brute(tm_handle *h, const LabelArgs &a, const int32_t *sel, const
     else       { if (nfma) TM_FIN_CASE(false, true); else TM_FIN_CASE(false, false); }
 #undef TM_FIN_CASE
     TM_CUDA(h, cudaGetLastError());
+    h->stats.launches += 2;                  // exhaustive kernel + its winner epilogue
     return TM_OK;
 }
 
@@ -395,6 +396,7 @@ int finalize_rows(tm_handle *h, const LabelArgs &a, const int32_t *win, const ui
     else       { if (nfma) TM_FINR_CASE(false, true); else TM_FINR_CASE(false, false); }
 #undef TM_FINR_CASE
     TM_KCHECK(h, a.stream, "finalize_rows_kernel");
+    h->stats.launches += 1;
     return TM_OK;
 }
 
@@ -421,6 +423,7 @@ int finish_pending(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win
     pending_winner_kernel<<<std::max(1, wgrid / 8), 256, 0, a.stream>>>(h->pend_idx.as<int32_t>(), h->brute_slots.as<uint32_t>(), &dst->n_brute,
                                                                        h->keys.as<unsigned long long>(), win);
     TM_KCHECK(h, a.stream, "pending_winner_kernel");
+    h->stats.launches += 2;
     return TM_OK;
 }
 

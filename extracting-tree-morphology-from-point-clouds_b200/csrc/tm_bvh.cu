@@ -396,6 +396,7 @@ int search_bvh(tm_handle *h, const LabelArgs &a, DevStats *dst, int32_t *win) {
     if (guard) { if (nfma) bvh_kernel<true, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<true, false><<<grid, 128, 0, a.stream>>>(b); }
     else       { if (nfma) bvh_kernel<false, true><<<grid, 128, 0, a.stream>>>(b); else bvh_kernel<false, false><<<grid, 128, 0, a.stream>>>(b); }
     TM_KCHECK(h, a.stream, "bvh_kernel");
+    h->stats.launches += 1;
     return TM_OK;
 }
 

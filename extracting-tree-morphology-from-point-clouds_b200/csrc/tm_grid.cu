@@ -1571,10 +1571,12 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     else       { if (nfma) TM_DIRECT_CASE(false, true); else TM_DIRECT_CASE(false, false); }
 #undef TM_DIRECT_CASE
     TM_KCHECK(h, st, "direct_kernel");
+    h->stats.launches += 1;
     const int ev_blocks = h->sm_count * 4;
     if (guard) { if (nfma) exact_kernel<true, true, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
     else       { if (nfma) exact_kernel<false, true, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<false, false, true><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
     TM_KCHECK(h, st, "exact_kernel");
+    h->stats.launches += 1;
 
     mark(h, 4, st);
     RingArgs rg;
@@ -1591,6 +1593,7 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
+    h->stats.launches += 1;
     int rc = search_bvh(h, a, dst, win);
     if (rc != TM_OK) return rc;
     mark(h, 5, st);
@@ -1651,15 +1654,18 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
                                                 h->pend_idx.as<int32_t>(), h->keys.as<unsigned long long>(),
                                                 h->brute_slots.as<uint32_t>(), dst);
     TM_KCHECK(h, st, "bin_count_kernel");
+    h->stats.launches += 1;
     mark(h, 1, st);
     int rc = run_scan(h, h->cells.as<uint32_t>(), ncodes, 1, h->cells.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
                       h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), h->items2.as<uint2>(),
                       h->warp_item.as<uint32_t>(), dst, st, nsub);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
+    h->stats.launches += 3;
     mark(h, 2, st);
     bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, h->cells.as<uint2>(), h->sorted_pts.as<float4>());
     TM_KCHECK(h, st, "bin_scatter_kernel");
+    h->stats.launches += 1;
 
     mark(h, 3, st);
     EvalArgs ev;
@@ -1698,9 +1704,11 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     if (wide) evaluate_kernel<true><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, 0, st>>>(ev);
     else evaluate_kernel<false><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, 0, st>>>(ev);
     TM_KCHECK(h, st, "evaluate_kernel");
+    h->stats.launches += 1;
     if (guard) { if (nfma) exact_kernel<true, true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
     else       { if (nfma) exact_kernel<false, true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<false, false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
     TM_KCHECK(h, st, "exact_kernel");
+    h->stats.launches += 1;
 
     // still uncertified at D_max (beyond the far part of their own tile): a handful of points -> ring search, one CTA per
     // point; many (clutter), or outside the grid -> per-point descent of the bounding-volume hierarchy
@@ -1719,6 +1727,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
     TM_KCHECK(h, st, "ring_kernel");
+    h->stats.launches += 1;
     rc = search_bvh(h, a, dst, win);
     if (rc != TM_OK) return rc;
 
