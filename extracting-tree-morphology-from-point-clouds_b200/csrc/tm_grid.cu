@@ -250,7 +250,7 @@ constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;     // 4096 voxels per block
 constexpr int PTS_PER_LANE = 2;           // points of ONE voxel a lane of the tile kernel owns (a "lane slot")
-constexpr int CELL_PAD = 4;               // uint2 slots per voxel cell: one 32-byte sector each, so that neighbouring voxels'
+constexpr int CELL_PAD = 4;               // uint2 slots per voxel cell for large clouds: one 32-byte sector each, so that neighbouring voxels'
                                           // atomics do not queue up on a shared sector
 
 struct Tri { uint32_t a, b, c; };
@@ -417,11 +417,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 
 static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mode, uint32_t *start, const uint32_t *tile_start,
                     const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, uint2 *items2, uint32_t *warp_item,
-                    DevStats *st, cudaStream_t stream, int nsub = 1) {
+                    DevStats *st, cudaStream_t stream, int nsub = 1, int pad = CELL_PAD) {
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
     Tri *bs = h->block_sums.as<Tri>();
-    const int stride = mode == 1 ? 2 * CELL_PAD : 1;
+    const int stride = mode == 1 ? 2 * pad : 1;
 #define TM_SCAN_CASE(S)                                                                                                        \
     do {                                                                                                                       \
         scan_reduce_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);                                \
@@ -634,7 +634,7 @@ __device__ __forceinline__ uint32_t point_code(const GridDev &g, float x, float 
 // that issues ONE atomic for the group.  A randomly ordered cloud gains nothing (no two lanes share a voxel, the match
 // costs a few instructions next to an L2 atomic); a spatially coherent one — tiled exports, scan lines, re-labelling a
 // sorted cloud — sends up to 32x fewer atomics.
-__global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub,
+__global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub, int pad,
                                                         uint2 *__restrict__ cells, int32_t *__restrict__ pend_idx,
                                                         unsigned long long *__restrict__ pend_keys,
                                                         uint32_t *__restrict__ brute_slots, DevStats *__restrict__ st) {
@@ -662,14 +662,14 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, code);
         // the warp's sub-cell: a function of the row index only, so that the scatter pass finds the same one
-        const size_t cell = (static_cast<size_t>(code) * nsub + (static_cast<uint32_t>(base >> 5) & (nsub - 1))) * CELL_PAD;
+        const size_t cell = (static_cast<size_t>(code) * nsub + (static_cast<uint32_t>(base >> 5) & (nsub - 1))) * pad;
         if (valid && lane == __ffs(peers) - 1) atomicAdd(&cells[cell].x, static_cast<uint32_t>(__popc(peers)));
     }
 }
 
 // pass 2: each point takes the next free slot of its voxel's run.  A cell is {cursor, run start}: one 64-bit atomic per
 // group of lanes advances the cursor by the group size and returns both words.
-__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub,
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub, int pad,
                                                           uint2 *__restrict__ cells, float4 *__restrict__ sorted) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const float *__restric
         unsigned long long cell = 0;
         if (valid && lane == leader)
             cell = atomicAdd(reinterpret_cast<unsigned long long *>(
-                                 cells + (static_cast<size_t>(code) * nsub + (static_cast<uint32_t>(base >> 5) & (nsub - 1))) * CELL_PAD),
+                                 cells + (static_cast<size_t>(code) * nsub + (static_cast<uint32_t>(base >> 5) & (nsub - 1))) * pad),
                              static_cast<unsigned long long>(__popc(peers)));
         cell = __shfl_sync(0xffffffffu, cell, leader);
         if (valid) {
@@ -1633,7 +1633,10 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
         if (density > 640.0) nsub = 8; else if (density > 320.0) nsub = 4; else if (density > 160.0) nsub = 2;
         if (const char *env = getenv("TM_SUBCELLS")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8) nsub = v; }
     }
-    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * CELL_PAD * nsub * (static_cast<size_t>(ncodes) + 1)));
+    // small clouds do not queue on the voxel counters: dense 8-byte cells (4x less to clear and to scan); large ones pad
+    // every cell to its own 32-byte sector
+    const int pad = n <= 3000000 ? 1 : CELL_PAD;
+    TM_CUDA(h, h->cells.ensure(sizeof(uint2) * pad * nsub * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
     TM_CUDA(h, h->items.ensure(sizeof(uint4) * (max_occ + 1)));
     TM_CUDA(h, h->items2.ensure(sizeof(uint2) * (max_occ + 1)));
@@ -1647,10 +1650,10 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     DevStats *dst = h->dstats.as<DevStats>();
     unsigned int *cursor = reinterpret_cast<unsigned int *>(h->dstats.as<unsigned char>() + sizeof(DevStats) + 16);
     TM_CUDA(h, cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats) + 64, st));
-    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * CELL_PAD * nsub * ncodes, st));
+    TM_CUDA(h, cudaMemsetAsync(h->cells.p, 0, sizeof(uint2) * pad * nsub * ncodes, st));
 
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
-    bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, h->cells.as<uint2>(),
+    bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, pad, h->cells.as<uint2>(),
                                                 h->pend_idx.as<int32_t>(), h->keys.as<unsigned long long>(),
                                                 h->brute_slots.as<uint32_t>(), dst);
     TM_KCHECK(h, st, "bin_count_kernel");
@@ -1658,12 +1661,12 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     mark(h, 1, st);
     int rc = run_scan(h, h->cells.as<uint32_t>(), ncodes, 1, h->cells.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
                       h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), h->items2.as<uint2>(),
-                      h->warp_item.as<uint32_t>(), dst, st, nsub);
+                      h->warp_item.as<uint32_t>(), dst, st, nsub, pad);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
     h->stats.launches += 3;
     mark(h, 2, st);
-    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, h->cells.as<uint2>(), h->sorted_pts.as<float4>());
+    bin_scatter_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, pad, h->cells.as<uint2>(), h->sorted_pts.as<float4>());
     TM_KCHECK(h, st, "bin_scatter_kernel");
     h->stats.launches += 1;
 

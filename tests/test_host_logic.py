@@ -61,3 +61,54 @@ def test_implicit_tree_numbering_used_by_the_device_bvh_build():
             for slot in range(1, slots):
                 got = slot_range(slot, n)
                 assert (got is None) == (slot not in want), (n, slot)
+
+
+def test_load_cloud_las_branch_with_a_stand_in_for_laspy(tmp_path, monkeypatch, capsys):
+    """The ``.las`` / ``.laz`` branch of load_cloud (reference Modules/Utils.py:237-245): laspy is not in this image, so a
+    stand-in with the two calls the branch makes (``laspy.open(path)`` as a context manager, ``.read()`` with ``x/y/z``) is
+    injected; without it the branch reports the missing library and returns None, as the reference does."""
+    from treemorph_b200.Modules import Utils
+    path = tmp_path / "cloud.laz"
+    path.write_bytes(b"not a real laz file")
+    xyz = np.array([[1.5, 2.5, 3.5], [4.0, 5.0, 6.0], [7.25, 8.25, 9.25]])
+
+    monkeypatch.setattr(Utils, "HAS_LASPY", False)
+    assert Utils.load_cloud(str(path)) is None
+    assert "laspy is not installed" in capsys.readouterr().out
+
+    class _Reader:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+        def read(self):
+            class _Las:
+                x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+            return _Las()
+
+    class _FakeLaspy:
+        opened = []
+
+        @staticmethod
+        def open(p):
+            _FakeLaspy.opened.append(p)
+            return _Reader()
+
+    monkeypatch.setattr(Utils, "laspy", _FakeLaspy)
+    monkeypatch.setattr(Utils, "HAS_LASPY", True)
+    for ext in (".laz", ".LAS"):
+        p = tmp_path / ("cloud" + ext)
+        p.write_bytes(b"x")
+        got = Utils.load_cloud(str(p))
+        assert got.dtype == np.float32 and got.shape == (3, 3) and np.array_equal(got, xyz.astype(np.float32))
+    assert len(_FakeLaspy.opened) == 2
+
+    class _Broken(_FakeLaspy):
+        @staticmethod
+        def open(p):
+            raise OSError("truncated file")
+    monkeypatch.setattr(Utils, "laspy", _Broken)
+    assert Utils.load_cloud(str(path)) is None                      # any failure: message + None, like the reference
+    assert "Failed to load point cloud" in capsys.readouterr().out
