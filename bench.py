@@ -204,7 +204,7 @@ def reference_arm(args):
 
 def load_ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of each per-call kernel at the default workload, from the
-    newest committed ncu --set full capture (profiles/*_dram_traffic.json, written by profiles/summarise.py together with the
+    newest committed ncu capture (profiles/*_dram_traffic.json, written by profiles/summarise.py together with the
     git hash of the build that was profiled).  None when there is no capture."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_dram_traffic.json")))
@@ -212,7 +212,7 @@ def load_ncu_traffic():
         return None
     with open(files[-1]) as f:
         d = json.load(f)
-    d["source"] = f"profiles/{os.path.basename(files[-1])} (ncu --set full, bytes per launch, build {d.get('git', '?')})"
+    d["source"] = f"profiles/{os.path.basename(files[-1])} (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, build {d.get('git', '?')})"
     return d
 
 

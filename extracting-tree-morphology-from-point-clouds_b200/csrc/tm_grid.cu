@@ -803,6 +803,8 @@ __device__ __forceinline__ uint32_t warp_append(bool want, unsigned int *counter
 constexpr int EV_BLOCKS_PER_SM = PTS_PER_LANE > 2 ? 3 : 4;
 constexpr uint32_t EV_CHUNK_ROUNDS = 4;        // consecutive rounds (groups of 32 lane slots) a warp takes per cursor fetch
 
+constexpr uint32_t EV_STAGE_CAP = 96;          // tile entries a warp stages per round: 96 x 32 B = 3 KB
+
 struct __align__(16) StageScratch {           // undecided points wait here until 32 of a kind can be written with one atomic
     uint4 front[64];
     uint4 back[64];
@@ -811,9 +813,16 @@ struct __align__(16) StageScratch {           // undecided points wait here unti
 template <bool WIDE>
 __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kernel(EvalArgs a) {
     __shared__ StageScratch stage[EV_WARPS];
+    __shared__ __align__(128) float4 tile_stage[EV_WARPS][2 * EV_STAGE_CAP];
+    __shared__ __align__(8) uint64_t tile_bar[EV_WARPS];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     StageScratch &sg = stage[threadIdx.x >> 5];
+    float4 *stage_tile = tile_stage[threadIdx.x >> 5];
+    uint64_t *bar = &tile_bar[threadIdx.x >> 5];
+    uint32_t bar_phase = 0;
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncwarp();
     const uint32_t n_items = a.st->work_items, total_slots = a.st->lane_slots;
     const uint32_t n_wslots = (total_slots + 31u) >> 5;
     // consecutive rounds per cursor fetch: 4 when every warp still gets several chunks, fewer for small clouds (a warp
@@ -884,9 +893,28 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
 #pragma unroll
             for (int q = 0; q < PTS_PER_LANE; ++q) pv[q] = valid && PTS_PER_LANE * k + q < it.w;
             const float4 *tile = a.tileAB + 2 * static_cast<size_t>(tile_off);
-            // the lane's tile is read entry by entry below: ask for all of its 128-byte lines now (lanes of one voxel ask
-            // for the same lines), so that the loop finds them in L1 instead of paying the L2 latency once per entry
-            if (a.pf & 1) for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
+            // ---- the near parts of the tiles this round touches (the warp's slots span n_dist consecutive items), staged
+            //      into the warp's shared-memory buffer with bulk asynchronous copies (TMA, one per tile, issued by the lane
+            //      that stands for the item) completing on the warp's mbarrier: one request per tile instead of one L2 round
+            //      trip per entry in the loop below.  Rounds whose tiles do not fit read them from global memory.
+            const uint32_t n_dist = __reduce_max_sync(0xffffffffu, valid ? lo + 1u : 0u);
+            uint32_t st_near = 0, st_off = 0;
+            if (lane < n_dist) { const uint4 di = a.items[it0 + lane]; st_off = di.x; st_near = di.y; }
+            uint32_t st_pos = st_near;                                  // inclusive scan of the near lengths
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, st_pos, o); if (lane >= static_cast<uint32_t>(o)) st_pos += v; }
+            const uint32_t st_total = __shfl_sync(0xffffffffu, st_pos, 31);
+            st_pos -= st_near;
+            const bool staged = st_total > 0u && st_total <= EV_STAGE_CAP;
+            if (staged) {
+                fence_proxy_async();                                    // the previous round's reads precede these writes
+                if (lane == 0) mbar_expect_tx(bar, st_total * 32u);
+                __syncwarp();
+                if (lane < n_dist && st_near) bulk_g2s(stage_tile + 2 * st_pos, a.tileAB + 2 * static_cast<size_t>(st_off), st_near * 32u, bar);
+            } else if (a.pf & 1) {
+                for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
+            }
+            const uint32_t my_pos = __shfl_sync(0xffffffffu, st_pos, lo);
             float4 P[PTS_PER_LANE];
             P[0] = pv[0] ? a.sorted[p0] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -911,18 +939,33 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
 #pragma unroll
             for (int q = 0; q < PTS_PER_LANE; ++q) tr[q] = Track{INF, INF, 0u};
             const uint32_t max_near = __reduce_max_sync(0xffffffffu, near_cnt);
-            float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
-            if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
-            for (uint32_t j = 0; j < max_near; j += 2) {
-                if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
-                if (j < near_cnt) {
+            if (staged) {
+                mbar_wait(bar, bar_phase);
+                bar_phase ^= 1u;
+                const float4 *mine_tile = stage_tile + 2 * my_pos;         // lanes of one voxel read the same words: broadcast
+#pragma unroll 2
+                for (uint32_t j = 0; j < max_near; ++j) {
+                    if (j < near_cnt) {
+                        const float4 A = mine_tile[2 * j], B = mine_tile[2 * j + 1];
 #pragma unroll
-                    for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A0, B0, band_lo, band_hi, S, rho2_min, j, tr[q]);
+                        for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A, B, band_lo, band_hi, S, rho2_min, j, tr[q]);
+                    }
                 }
-                if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
-                if (j + 1u < near_cnt) {
+                __syncwarp();                                               // everyone is done with the buffer
+            } else {
+                float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
+                if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
+                for (uint32_t j = 0; j < max_near; j += 2) {
+                    if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
+                    if (j < near_cnt) {
 #pragma unroll
-                    for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, tr[q]);
+                        for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A0, B0, band_lo, band_hi, S, rho2_min, j, tr[q]);
+                    }
+                    if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
+                    if (j + 1u < near_cnt) {
+#pragma unroll
+                        for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, tr[q]);
+                    }
                 }
             }
             uint32_t npts = 0;
