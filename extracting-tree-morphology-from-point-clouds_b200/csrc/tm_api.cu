@@ -325,6 +325,9 @@ int tm_destroy(tm_handle *h) {
         h->pinned_out[i].release();
     }
     if (h->small_stream) cudaStreamDestroy(h->small_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+    if (h->join_ev) cudaEventDestroy(h->join_ev);
     delete h->pool;
     for (auto &b : h->chunk_packed) b.release();
     for (auto &s : h->pipe_stream) if (s) cudaStreamDestroy(s);

@@ -356,7 +356,7 @@ finalize_rows_kernel(const float *__restrict__ pts, int64_t n, int64_t row_strid
         for (int k = 0; k < R; ++k) {
             row[k] = row0 + k * span;
             ok[k] = row[k] < n;
-            if (rows) row[k] = rows[ok[k] ? row[k] : row0];
+            if (rows) row[k] = rows[ok[k] ? row[k] : row0] & 0x3fffffffu;        // pending slots carry two flag bits
             const int64_t r = (ok[k] || rows) ? row[k] : row0;
             j[k] = static_cast<uint32_t>(win[r]);
             const float *p = pts + r * row_stride;

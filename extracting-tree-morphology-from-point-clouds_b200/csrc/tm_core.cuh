@@ -174,6 +174,10 @@ struct tm_handle {
     // ---- point features (tm_knn.cu) ----
     tmn::DevBuf knn_cells, knn_start, knn_sorted, knn_box;
 
+    // ---- overlapped epilogue (tm_grid.cu) ----
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+
     // ---- multi-GPU (tm_comm.cu) ----
     void *comm = nullptr;            // ncclComm_t
     int32_t comm_rank = 0, comm_size = 0;

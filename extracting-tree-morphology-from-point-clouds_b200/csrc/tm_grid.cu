@@ -637,7 +637,8 @@ __device__ __forceinline__ uint32_t point_code(const GridDev &g, float x, float 
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ pts, int64_t n, int64_t row_stride, GridDev g, int nsub, int pad,
                                                         uint2 *__restrict__ cells, int32_t *__restrict__ pend_idx,
                                                         unsigned long long *__restrict__ pend_keys,
-                                                        uint32_t *__restrict__ brute_slots, DevStats *__restrict__ st) {
+                                                        uint32_t *__restrict__ brute_slots, int32_t *__restrict__ win,
+                                                        DevStats *__restrict__ st) {
     const int lane = threadIdx.x & 31;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t base = blockIdx.x * static_cast<int64_t>(blockDim.x) + (threadIdx.x & ~31); base < n; base += stride) {
@@ -657,6 +658,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
                 const unsigned int s = atomicAdd(&st->pending, 1u);
                 pend_idx[s] = static_cast<int32_t>(i) | OUTSIDE_BIT;
                 pend_keys[s] = KEY_NONE;
+                win[i] = 0;                                             // provisional: the overlapped epilogue may read it
                 if (!(fabsf(x) + fabsf(y) + fabsf(z) < 3.0e38f)) brute_slots[atomicAdd(&st->n_brute, 1u)] = s;
             }
         }
@@ -1003,6 +1005,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
                     if (pend) {
                         a.pend_idx[sp] = __float_as_int(P[q].w);
                         a.pend_keys[sp] = KEY_NONE;
+                        a.win[__float_as_int(P[q].w)] = 0;              // provisional: the overlapped epilogue may read it
                     }
                 }
             }
@@ -1177,6 +1180,7 @@ __device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, 
     if (pend) {
         a.pend_idx[sp] = __float_as_int(P.w);
         a.pend_keys[sp] = key;
+        a.win[__float_as_int(P.w)] = key == KEY_NONE ? 0 : static_cast<int32_t>(key_index(key));     // provisional
     }
     __syncwarp();                    // ws.P / ws.best are rewritten by the next task
 }
@@ -1550,6 +1554,11 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
 // (scan over every voxel of the grid, a dozen launches), the direct path pays ~0.25 us per 1000 points for its uncoalesced
 // tile reads.  Measured crossover on a randomly ordered cloud against 50k cylinders: ~800k points
 // (profiles/r02_floor_phases.json); TM_DIRECT=0/1 forces either.
+static bool overlap_enabled() {
+    static const bool on = [] { const char *e = getenv("TM_OVERLAP"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 static bool use_direct(const tm_handle *, const LabelArgs &a) {
     static const int forced = [] { const char *e = getenv("TM_DIRECT"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced != 0;
@@ -1698,7 +1707,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const int pt_blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, static_cast<size_t>(h->sm_count) * 32));
     bin_count_kernel<<<pt_blocks, 256, 0, st>>>(a.pts, a.n, a.row_stride, g, nsub, pad, h->cells.as<uint2>(),
                                                 h->pend_idx.as<int32_t>(), h->keys.as<unsigned long long>(),
-                                                h->brute_slots.as<uint32_t>(), dst);
+                                                h->brute_slots.as<uint32_t>(), a.out_index ? a.out_index : h->win.as<int32_t>(), dst);
     TM_KCHECK(h, st, "bin_count_kernel");
     h->stats.launches += 1;
     mark(h, 1, st);
@@ -1757,7 +1766,28 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     h->stats.launches += 1;
 
     // still uncertified at D_max (beyond the far part of their own tile): a handful of points -> ring search, one CTA per
-    // point; many (clutter), or outside the grid -> per-point descent of the bounding-volume hierarchy
+    // point; many (clutter), or outside the grid -> per-point descent of the bounding-volume hierarchy.
+    // These kernels are latency chains over a handful of points while the epilogue streams over every row, so the two run
+    // side by side: the stragglers are searched on the handle's high-priority side stream, the epilogue of ALL rows runs on
+    // the caller's stream as soon as the exact kernel is done (every pending row already holds a valid provisional winner),
+    // and once both are through a short list epilogue rewrites the outputs of exactly the pending rows.  (Serial when the phases are
+    // being timed, so that the per-phase numbers keep their meaning.)
+    const bool overlap = !h->profiling && overlap_enabled();
+    cudaStream_t ss = st;                     // stream of the straggler kernels
+    LabelArgs as = a;
+    if (overlap) {
+        if (!h->side_stream) {
+            int lo_prio = 0, hi_prio = 0;
+            TM_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            TM_CUDA(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi_prio));     // few CTAs, long chains: first in line
+        }
+        if (!h->fork_ev) TM_CUDA(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+        if (!h->join_ev) TM_CUDA(h, cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+        TM_CUDA(h, cudaEventRecord(h->fork_ev, st));
+        TM_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->fork_ev, 0));
+        ss = h->side_stream;
+        as.stream = ss;
+    }
     mark(h, 4, st);
     RingArgs rg;
     rg.pts = a.pts; rg.row_stride = a.row_stride;
@@ -1770,20 +1800,27 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     rg.st = dst;
     // one CTA per pending point; far fewer points than rows ever reach it, so small calls get a small grid
     const int rg_blocks = static_cast<int>(std::min<size_t>(static_cast<size_t>(h->sm_count) * (2048 / (RING_WARPS * 32)), std::max<size_t>(h->sm_count, n / 256)));
-    if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
-    else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, st>>>(rg, g); }
-    TM_KCHECK(h, st, "ring_kernel");
+    if (guard) { if (nfma) ring_kernel<true, true><<<rg_blocks, RING_WARPS * 32, 0, ss>>>(rg, g); else ring_kernel<true, false><<<rg_blocks, RING_WARPS * 32, 0, ss>>>(rg, g); }
+    else       { if (nfma) ring_kernel<false, true><<<rg_blocks, RING_WARPS * 32, 0, ss>>>(rg, g); else ring_kernel<false, false><<<rg_blocks, RING_WARPS * 32, 0, ss>>>(rg, g); }
+    TM_KCHECK(h, ss, "ring_kernel");
     h->stats.launches += 1;
-    rc = search_bvh(h, a, dst, win);
+    rc = search_bvh(h, as, dst, win);
     if (rc != TM_OK) return rc;
 
     // exhaustive search for non-finite points, then the winning rows of every pending point
     mark(h, 5, st);
-    rc = finish_pending(h, a, dst, win, h->maxabs);
+    rc = finish_pending(h, as, dst, win, h->maxabs);
     if (rc != TM_OK) return rc;
 
-    // winner-only epilogue of every row: label + offset, streaming
+    // winner-only epilogue: label + offset, streaming
     mark(h, 7, st);
+    if (overlap) {
+        TM_CUDA(h, cudaEventRecord(h->join_ev, ss));
+        rc = finalize_rows(h, a, win, nullptr, nullptr);                       // every row, on the caller's stream
+        if (rc != TM_OK) return rc;
+        TM_CUDA(h, cudaStreamWaitEvent(st, h->join_ev, 0));
+        return finalize_rows(h, a, win, reinterpret_cast<const uint32_t *>(h->pend_idx.as<int32_t>()), &dst->pending);
+    }
     return finalize_rows(h, a, win, nullptr, nullptr);
 }
 
