@@ -745,7 +745,6 @@ struct EvalArgs {
     const float *tileLB;
     float atol, eps, slack, near, reach;
     float amb;                    // S of the estimate comparison (<= slack)
-    int pf;                       // L1 prefetch switches (experiments): 1 own tile, 2 next round's points / items, 4 tiles ahead
     uint4 *undecided;             // points the estimates could not decide: {sorted position, item, bits(upper bound), 0};
     uint32_t undecided_cap;       //   near-certified ones fill the array from the front, the others from the back
     int32_t *win;                 // winning cylinder row of every certified point, at the point's original row
@@ -832,7 +831,6 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
     const uint32_t n_warps = gridDim.x * EV_WARPS;
     const uint32_t chunk_rounds = n_wslots >= 16u * n_warps ? EV_CHUNK_ROUNDS : (n_wslots >= 4u * n_warps ? 2u : 1u);
     const uint32_t n_chunks = (n_wslots + chunk_rounds - 1u) / chunk_rounds;
-    const uint32_t n_sorted = static_cast<uint32_t>(a.st->points_binned);
     const float S = a.amb;
     const float band_hi = a.atol + S, band_lo = a.atol - S, rho2_min = S * S;
     const bool lists = (a.n_special | a.n_long | a.n_aligned) != 0u;     // warp-uniform: every point takes the exact kernel
@@ -913,29 +911,12 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
                 if (lane == 0) mbar_expect_tx(bar, st_total * 32u);
                 __syncwarp();
                 if (lane < n_dist && st_near) bulk_g2s(stage_tile + 2 * st_pos, a.tileAB + 2 * static_cast<size_t>(st_off), st_near * 32u, bar);
-            } else if (a.pf & 1) {
-                for (uint32_t e = 0; e < near_cnt; e += 4) prefetch_l1(tile + 2 * e);
             }
             const uint32_t my_pos = __shfl_sync(0xffffffffu, st_pos, lo);
             float4 P[PTS_PER_LANE];
             P[0] = pv[0] ? a.sorted[p0] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int q = 1; q < PTS_PER_LANE; ++q) P[q] = pv[q] ? a.sorted[p0 + q] : P[0];
-            // the following rounds of the chunk continue where this one ends, in the sorted cloud and in the item arrays:
-            // their lines can be asked for now (no address depends on anything still in flight) — points two rounds ahead,
-            // item records one round ahead, and the tiles of the next few items as soon as their records are here (below)
-            uint2 ahead = make_uint2(0u, 0u);
-            if ((a.pf & 2) && cur + 1u < r_end) {
-                constexpr uint32_t RP = 32 * PTS_PER_LANE;                  // points per round, at most
-                const uint32_t p_end = __reduce_max_sync(0xffffffffu, valid ? p0 + PTS_PER_LANE : 0u);
-                const uint32_t i_end = __reduce_max_sync(0xffffffffu, valid ? item : 0u);
-                const uint32_t p_from = p_end + (cur == chunk * chunk_rounds ? 0u : RP);       // first round of a chunk: both
-                if (lane < RP / 4) { if (p_from + 8u * lane < n_sorted) prefetch_l1(a.sorted + p_from + 8u * lane); }
-                if (lane >= 16 && lane < 20) { if (i_end + 8u * (lane - 16u) < n_items) prefetch_l1(a.items + i_end + 8u * (lane - 16u)); }
-                else if (lane >= 20 && lane < 22) { if (i_end + 16u * (lane - 20u) < n_items) prefetch_l1(a.items2 + i_end + 16u * (lane - 20u)); }
-                else if ((a.pf & 4) && lane >= 22 && lane < 28) { if (i_end + (lane - 21u) < n_items) { const uint4 nx = a.items[i_end + (lane - 21u)]; ahead = make_uint2(nx.x, nx.y); } }
-            }
-
             // ---- estimates over the near part of the lane's own tile, entries double-buffered in registers
             Track tr[PTS_PER_LANE];
 #pragma unroll
@@ -974,7 +955,6 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
 #pragma unroll
             for (int q = 0; q < PTS_PER_LANE; ++q) npts += pv[q] ? 1u : 0u;
             bounds += near_cnt * npts;
-            for (uint32_t e = 0; e < min(ahead.y, 12u); e += 4) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(ahead.x + e));
 
             // ---- decided by the estimates alone?  (d1 = NaN without a reliable entry: every comparison below fails)
             float up[PTS_PER_LANE];
@@ -1591,8 +1571,6 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     ev.tileLB = h->tileLB.as<float>();
     ev.atol = a.prm.perp_atol; ev.eps = a.prm.norm_eps;
     ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
-    ev.pf = 3;
-    if (const char *env = getenv("TM_PF")) ev.pf = atoi(env);
     ev.amb = slack;
     if (const char *env = getenv("TM_AMB_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v > 0.f && v <= 1.f) ev.amb = slack * v; }
     int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();
@@ -1740,8 +1718,6 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.slack = slack; ev.near = h->near; ev.reach = h->reach;
     // allowance of the estimate-vs-reference comparison: the same rounding slack by default (TM_AMB_FACTOR scales it down
     // for experiments; never above the slack)
-    ev.pf = 3;
-    if (const char *env = getenv("TM_PF")) ev.pf = atoi(env);
     ev.amb = slack;
     if (const char *env = getenv("TM_AMB_FACTOR")) { const float v = static_cast<float>(atof(env)); if (v > 0.f && v <= 1.f) ev.amb = slack * v; }
     int32_t *win = a.out_index ? a.out_index : h->win.as<int32_t>();       // the caller's index array doubles as the scatter target
