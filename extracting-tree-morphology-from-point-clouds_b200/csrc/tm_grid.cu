@@ -804,7 +804,7 @@ __device__ __forceinline__ uint32_t warp_append(bool want, unsigned int *counter
 constexpr int EV_BLOCKS_PER_SM = PTS_PER_LANE > 2 ? 3 : 4;
 constexpr uint32_t EV_CHUNK_ROUNDS = 4;        // consecutive rounds (groups of 32 lane slots) a warp takes per cursor fetch
 
-constexpr uint32_t EV_STAGE_CAP = 96;          // tile entries a warp stages per round: 96 x 32 B = 3 KB
+constexpr uint32_t EV_STAGE_CAP = 144;         // tile entries a warp stages per round: 144 x 32 B = 4.5 KB (dynamic shared memory)
 
 struct __align__(16) StageScratch {           // undecided points wait here until 32 of a kind can be written with one atomic
     uint4 front[64];
@@ -814,12 +814,12 @@ struct __align__(16) StageScratch {           // undecided points wait here unti
 template <bool WIDE>
 __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kernel(EvalArgs a) {
     __shared__ StageScratch stage[EV_WARPS];
-    __shared__ __align__(128) float4 tile_stage[EV_WARPS][2 * EV_STAGE_CAP];
+    extern __shared__ __align__(128) unsigned char tile_stage_raw[];          // EV_WARPS x 2 x EV_STAGE_CAP float4
     __shared__ __align__(8) uint64_t tile_bar[EV_WARPS];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     StageScratch &sg = stage[threadIdx.x >> 5];
-    float4 *stage_tile = tile_stage[threadIdx.x >> 5];
+    float4 *stage_tile = reinterpret_cast<float4 *>(tile_stage_raw) + static_cast<size_t>(threadIdx.x >> 5) * 2 * EV_STAGE_CAP;
     uint64_t *bar = &tile_bar[threadIdx.x >> 5];
     uint32_t bar_phase = 0;
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -1732,8 +1732,14 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const bool wide = a.prm.perp_atol > 2.f * ev.amb;
     if (guard) ev.n_aligned = 0;              // variant B never yields NaN on an axis line
     const int ev_blocks = h->sm_count * 4;
-    if (wide) evaluate_kernel<true><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, 0, st>>>(ev);
-    else evaluate_kernel<false><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, 0, st>>>(ev);
+    const size_t stage_bytes = sizeof(float4) * 2 * EV_STAGE_CAP * EV_WARPS;
+    if (wide) {
+        TM_CUDA(h, cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
+        evaluate_kernel<true><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, stage_bytes, st>>>(ev);
+    } else {
+        TM_CUDA(h, cudaFuncSetAttribute(evaluate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
+        evaluate_kernel<false><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, stage_bytes, st>>>(ev);
+    }
     TM_KCHECK(h, st, "evaluate_kernel");
     h->stats.launches += 1;
     if (guard) { if (nfma) exact_kernel<true, true, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); else exact_kernel<true, false, false><<<ev_blocks, EV_WARPS * 32, 0, st>>>(ev); }
