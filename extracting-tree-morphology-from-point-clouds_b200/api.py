@@ -444,6 +444,36 @@ class Engine:
         return float(v.value)
 
 
+def comm_init_all(engines: list[Engine]) -> None:
+    """One process driving several devices: one communicator over the engines' devices (tm_comm_init_all)."""
+    lib = B.load()
+    arr = (ctypes.c_void_p * len(engines))(*[e._h for e in engines])
+    B.check(lib, engines[0]._h, lib.tm_comm_init_all(arr, len(engines)))
+
+
+def broadcast_cylinders_all(engines: list[Engine], start, radius, axis_length, axis_unit, ids=None, root_index: int = 0) -> None:
+    """Replicate the table held on engines[root_index]'s device on every engine of the communicator and install it
+    (tm_broadcast_cylinders_all)."""
+    lib = B.load()
+    root = engines[root_index]
+    start = root._f32(start, 3)
+    unit = root._f32(axis_unit, 3)
+    m = start.shape[0]
+    length = root._f32(axis_length).reshape(-1)
+    radius = root._f32(radius).reshape(-1)
+    if ids is not None:
+        ids = torch.as_tensor(ids).to(device=root.device, dtype=torch.int32).reshape(-1)
+    torch.cuda.synchronize(root.device)
+    arr = (ctypes.c_void_p * len(engines))(*[e._h for e in engines])
+    B.check(lib, root._h, lib.tm_broadcast_cylinders_all(
+        arr, len(engines), _ptr(start), start.stride(0), start.stride(1), _ptr(unit), unit.stride(0), unit.stride(1),
+        _ptr(length), length.stride(0) if m else 1, _ptr(radius), radius.stride(0) if m else 1,
+        _ptr(ids), (ids.stride(0) if m else 1) if ids is not None else 1, m, int(root_index)))
+    for e in engines:
+        e.m = m
+        e.installs += 1
+
+
 _engines: dict[int, Engine] = {}
 
 

@@ -8,6 +8,7 @@ Tolerances (BASELINE.json north_star): cylinder indices exact except near-ties (
 1e-6 relative); offsets and distances within 1e-5 m.  In practice the kernels are bit-identical.
 """
 import gc
+import os
 
 import numpy as np
 import pandas as pd
@@ -639,3 +640,76 @@ def test_full_size_properties_variant_b(eng):
     again = eng.label(dpts[perm], api.VARIANT_B, mode="grid", want=("index", "dist"))
     assert bool((again["index"] == full["index"][perm]).all())
     assert bool((again["dist"] == full["dist"][perm]).all())
+
+
+# ---- round-2 entry points -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("f64", [False, True])
+def test_wide_records_are_the_seven_columns_plus_the_tail(eng, f64):
+    """tm_label_cloud_host_wide: the (N,11) rows the drivers save (LabelGenerationCuda.py:196-205) are the (N,7) record with
+    the tail values appended, for float32 / float64 clouds with extra columns and a ragged last chunk."""
+    case = make_case(700, 50_003, seed=81, variant="A")
+    _install(eng, case)
+    pts = case["points"]
+    cloud = np.concatenate([pts.astype(np.float64) if f64 else pts, np.full((len(pts), 1), 3, np.float64 if f64 else pts.dtype)], axis=1)
+    rec7 = eng.label_cloud_host(cloud, api.VARIANT_A, mode="grid")
+    wide, dist = eng.label_cloud_host(cloud, api.VARIANT_A, mode="grid", tail=(1.0, 1.0, 1.0, 1.0), want_dist=True)
+    assert wide.shape == (len(pts), 11) and wide.dtype == np.float64
+    assert np.array_equal(wide[:, :7], rec7, equal_nan=True) and (wide[:, 7:] == 1.0).all()
+    ora = oracle_label(case, pts)
+    assert np.array_equal(dist, ora["dist"], equal_nan=True) and np.array_equal(wide[:, 6], ora["id"].astype(np.float64))
+    odd = eng.label_cloud_host(cloud, api.VARIANT_A, mode="grid", tail=(0.5, -2.0))
+    assert odd.shape == (len(pts), 9) and (odd[:, 7] == 0.5).all() and (odd[:, 8] == -2.0).all()
+    with pytest.raises(ValueError):
+        eng.label_cloud_host(cloud, api.VARIANT_A, tail=tuple(range(9)))             # rows of more than 15 doubles
+
+
+def test_stats_of_the_estimate_path_and_host_probe(eng):
+    from treemorph_b200 import synth
+    q = synth.random_qsm(5000, seed=91)
+    pts = synth.sample_points(q, 800_000, seed=92)                                     # above the direct path's limit: sorted path
+    start, radius, length, unit, ids = synth.cylinder_arrays(q)
+    case = {"start": start, "radius": radius, "length": length, "unit": unit, "ids": ids, "variant": _oracle.VARIANT_A, "points": pts}
+    _install(eng, case)
+    eng.label(torch.tensor(pts, device=eng.device), api.VARIANT_A, mode="grid")
+    st = eng.stats()
+    assert st["launches"] >= 10 and st["lane_ops_per_bound"] == 33
+    assert st["bound_tests"] > 5 * len(pts) and 0 < st["points_slow"] < 0.3 * len(pts)
+    assert st["pairs_evaluated"] < 1.0 * len(pts)                                      # far fewer exact evaluations than points
+    assert st["points_grid"] + st["points_far"] + st["points_ring"] + st["points_tree"] + st["points_brute"] == len(pts)
+    bw = eng.host_bandwidth()
+    assert bw["threads"] >= 1 and 1e9 < bw["bytes_per_s"] < 5e12
+
+
+def test_direct_and_sorted_paths_agree_in_fresh_processes(tmp_path):
+    """TM_DIRECT is read once per process: label the same clutter-laden cloud with the sort-free path forced and forbidden
+    in two subprocesses and compare every output bit."""
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import sys, numpy as np, torch
+        sys.path.insert(0, {root!r})
+        from treemorph_b200 import api, synth
+        q = synth.random_qsm(3000, seed=71)
+        pts = synth.sample_points(q, 150_000, seed=72)
+        rng = np.random.default_rng(73)
+        pts[::7] += rng.normal(0, 2.0, size=pts[::7].shape).astype(np.float32)          # clutter metres away
+        pts[5] = [np.nan, 0, 0]; pts[6] = [1e30, 1e30, 1e30]
+        s, r, l, u, i = synth.cylinder_arrays(q)
+        dev = torch.device("cuda", 0)
+        e = api.Engine(dev)
+        e.set_cylinders(*[torch.tensor(x, device=dev) for x in (s, r, l, u)], torch.tensor(i, device=dev))
+        for vn in "AB":
+            got = e.label(torch.tensor(pts, device=dev), api.VARIANTS[vn], mode="grid")
+            np.savez(sys.argv[1] + vn + ".npz", **{{k: v.cpu().numpy() for k, v in got.items()}})
+    """)
+    outs = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, TM_DIRECT=flag)
+        prefix = str(tmp_path / f"d{flag}_")
+        subprocess.run([sys.executable, "-c", code, prefix], check=True, env=env, timeout=600)
+        outs[flag] = {vn: dict(np.load(prefix + vn + ".npz")) for vn in "AB"}
+    for vn in "AB":
+        for k in ("index", "id", "dist", "offset"):
+            a, b = outs["0"][vn][k], outs["1"][vn][k]
+            assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"variant {vn}: {k} differs between the two paths"

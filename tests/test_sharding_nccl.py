@@ -123,3 +123,31 @@ def test_broadcast_without_a_communicator_is_an_install():
     want = oracle.label(pts, start, radius, length, unit, ids, oracle.VARIANT_A)
     assert (got["id"].cpu().numpy() == want["id"]).all()
     eng.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_one_process_two_devices_init_all_and_broadcast_all():
+    """tm_comm_init_all / tm_broadcast_cylinders_all: one process, one handle per device; the table lives on device 0 only and
+    both devices label their rows of the cloud bit-identically to the oracle."""
+    from treemorph_b200 import api, sharding, synth
+    from oracle import oracle
+    engines = [api.Engine(torch.device("cuda", i)) for i in range(2)]
+    api.comm_init_all(engines)
+    assert [e.comm_info() for e in engines] == [(0, 2), (1, 2)]
+    q = synth.random_qsm(2500, seed=51, id_offset=3)
+    start, radius, length, unit, ids = synth.cylinder_arrays(q)
+    d0 = engines[0].device
+    api.broadcast_cylinders_all(engines, torch.tensor(start, device=d0), torch.tensor(radius, device=d0), torch.tensor(length, device=d0),
+                                torch.tensor(unit, device=d0), torch.tensor(ids, device=d0), root_index=0)
+    pts = synth.sample_points(q, 40_000, seed=52)
+    want = oracle.label(pts, start, radius, length, unit, ids, oracle.VARIANT_A)
+    for r, e in enumerate(engines):
+        lo, hi = sharding.shard_bounds(len(pts), 2, r)
+        with torch.cuda.device(e.device):
+            got = e.label(torch.tensor(pts[lo:hi], device=e.device), api.VARIANT_A, mode="grid")
+            torch.cuda.synchronize()
+        assert (got["id"].cpu().numpy() == want["id"][lo:hi]).all()
+        assert np.array_equal(got["dist"].cpu().numpy(), want["dist"][lo:hi], equal_nan=True)
+    for e in engines:
+        e.comm_destroy()
+        e.close()
