@@ -1166,6 +1166,7 @@ __device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, 
 }
 
 constexpr int EXACT_FAR_LANES = 8;
+constexpr uint32_t EXACT_FAR_WIDE_BELOW = 100000;       // far walks use 8 lanes per point while there are few of them (latency), 1 beyond (throughput)
 
 template <bool GUARD, bool NFMA, bool DIRECT>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
@@ -1174,14 +1175,19 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
     const uint32_t lt = (1u << lane) - 1u;
     ExactScratch &ws = scratch[warp];
     const uint32_t n_front = a.st->undecided_near, n_back = a.st->undecided_far;
-    constexpr uint32_t PB = 32 / EXACT_FAR_LANES;
+    const bool wide_far = n_back < EXACT_FAR_WIDE_BELOW;                       // grid-uniform
+    const uint32_t PB = wide_far ? 32u / EXACT_FAR_LANES : 32u;
     const uint32_t w_front = (n_front + 31u) >> 5, w_all = w_front + (n_back + PB - 1u) / PB;
     unsigned int pairs = 0, culls = 0, nfar = 0;
     uint32_t qn = 0;
     // the long walks first: they are the critical path of a small call
     for (uint32_t w = blockIdx.x * EV_WARPS + warp; w < w_all; w += gridDim.x * EV_WARPS) {
-        if (w < w_all - w_front) exact_task<GUARD, NFMA, DIRECT, EXACT_FAR_LANES>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
-        else exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w - (w_all - w_front), true, n_front, qn, pairs, culls, nfar);
+        if (w < w_all - w_front) {
+            if (wide_far) exact_task<GUARD, NFMA, DIRECT, EXACT_FAR_LANES>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
+            else exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
+        } else {
+            exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w - (w_all - w_front), true, n_front, qn, pairs, culls, nfar);
+        }
     }
     unsigned long long all_culls = culls;
 #pragma unroll
