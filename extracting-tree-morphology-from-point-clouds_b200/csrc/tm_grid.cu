@@ -772,8 +772,8 @@ __device__ __forceinline__ void bound_pair(float px, float py, float pz, const f
     const float tc = fminf(fmaxf(t, 0.f), A.w);
     const float d = t - tc;
     const float rx = fmaf(-t, B.x, vx), ry = fmaf(-t, B.y, vy), rz = fmaf(-t, B.z, vz);     // rejection from the axis LINE
-    const float rho2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
-    const float rho = rho2 * mufu_rsq(fmaxf(rho2, 1e-30f));
+    const float rho2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1e-30f)));       // + 1e-30: rsqrt stays finite on the axis line
+    const float rho = rho2 * mufu_rsq(rho2);
     const float a = rho - B.w;
     const float ad = fabsf(d);
     const bool beyond = ad > band_hi;                       // certainly not perp
