@@ -311,7 +311,7 @@ int tm_destroy(tm_handle *h) {
     cudaDeviceSynchronize();
     tmn::DevBuf *bufs[] = {&h->recA, &h->recB, &h->recAB, &h->cells, &h->bvh_nodes, &h->bvh_rows, &h->bvh_leafAB, &h->knn_cells, &h->knn_start, &h->knn_sorted, &h->knn_box, &h->ids, &h->boxlo, &h->boxhi, &h->bbox, &h->cyl_cell_start, &h->cyl_cell_cnt,
                           &h->cyl_cell_near, &h->tileLB, &h->tile_keys, &h->long_list, &h->special, &h->aligned, &h->keys, &h->cell_count,
-                          &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileAB, &h->tileI, &h->items, &h->items2, &h->warp_item, &h->undecided, &h->late_rows, &h->tile_desc,
+                          &h->cell_start, &h->block_sums, &h->sorted_pts, &h->tileAB, &h->tileI, &h->items, &h->warp_item, &h->undecided, &h->late_rows, &h->tile_desc,
                           &h->pend_idx, &h->brute_slots, &h->win, &h->dstats, &h->scratch_f, &h->cloud_res, &h->small_in,
                           &h->small_out, &h->bvh_scratch};
     tm_comm_destroy(h);

@@ -141,8 +141,7 @@ struct tm_handle {
     tmn::DevBuf cell_count, cell_start, block_sums;      // index build (cell_count / cell_start) and scan partials
     tmn::DevBuf cells;               // uint2 per voxel: {point count -> scatter cursor, first sorted point}
     tmn::DevBuf sorted_pts;          // float4 per point {x,y,z,bits(original row)}
-    tmn::DevBuf items;               // uint4 per occupied voxel {tile offset, near length, first sorted point, point count}
-    tmn::DevBuf items2;              // uint2 per occupied voxel {far length, first lane slot}
+    tmn::DevBuf items;               // 2 x uint4 per occupied voxel {tile offset, near length, first sorted point, point count} {far length, first lane slot, -, -}
     tmn::DevBuf warp_item;           // uint32 per group of 32 lane slots: the item its first slot belongs to
     tmn::DevBuf undecided;           // uint4 per point the estimates left undecided (exact kernel's work list)
     tmn::DevBuf late_rows;           // uint32: rows the direct kernel did not finish itself

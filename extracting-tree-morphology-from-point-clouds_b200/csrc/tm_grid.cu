@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(Tri *__restri
 // own cells, then rewrites them as {0, start} — the low word becomes the scatter pass's cursor, so that ONE 64-bit
 // atomicAdd returns both the run start and the slot inside the run.
 // mode 1 (points): start[code] = first sorted point of the voxel; every occupied voxel becomes one item
-// {tile offset, near length, first point, point count} + {far length, first lane slot}, in voxel-id order, and every
+// (32 bytes: {tile offset, near length, first point, point count | far length, first lane slot, -, -}), in voxel-id order, and every
 // group of 32 lane slots learns which item its first slot belongs to (warp_item).
 template <int NSUB>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t *count, int stride, uint32_t ncodes,
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
                                                                   const uint32_t *__restrict__ tile_start,
                                                                   const uint32_t *__restrict__ tile_cnt,
                                                                   const uint32_t *__restrict__ tile_near,
-                                                                  uint4 *__restrict__ items, uint2 *__restrict__ items2,
+                                                                  uint4 *__restrict__ items,
                                                                   uint32_t *__restrict__ warp_item) {
     const int lane = threadIdx.x & 31;
     const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
@@ -391,8 +391,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
                 }
                 if (cnt[i]) {
                     const uint32_t tnear = tile_near[base + i];
-                    items[run.b] = make_uint4(tile_start[base + i], tnear, run.a, cnt[i]);
-                    items2[run.b] = make_uint2(tile_cnt[base + i] - tnear, run.c);
+                    items[2 * run.b] = make_uint4(tile_start[base + i], tnear, run.a, cnt[i]);
+                    items[2 * run.b + 1] = make_uint4(tile_cnt[base + i] - tnear, run.c, 0u, 0u);
                     const uint32_t nslots = (cnt[i] + PTS_PER_LANE - 1) / PTS_PER_LANE;
                     q_lo = (run.c + 31u) >> 5;
                     q_hi = (run.c + nslots - 1u) >> 5;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t
 }
 
 static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mode, uint32_t *start, const uint32_t *tile_start,
-                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, uint2 *items2, uint32_t *warp_item,
+                    const uint32_t *tile_cnt, const uint32_t *tile_near, uint4 *items, uint32_t *warp_item,
                     DevStats *st, cudaStream_t stream, int nsub = 1, int pad = CELL_PAD) {
     const uint32_t nblocks = (ncodes + SCAN_BLOCK - 1) / SCAN_BLOCK;
     TM_CUDA(h, h->block_sums.ensure(sizeof(Tri) * nblocks));
@@ -427,7 +427,7 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
         scan_reduce_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs);                                \
         scan_blocks_kernel<<<1, SCAN_THREADS, 0, stream>>>(bs, nblocks, st);                                                   \
         scan_apply_kernel<S><<<nblocks, SCAN_THREADS, 0, stream>>>(count, stride, ncodes, bs, mode, start, tile_start, tile_cnt, \
-                                                                   tile_near, items, items2, warp_item);                       \
+                                                                   tile_near, items, warp_item);                               \
     } while (0)
     switch (nsub) {
         case 2: TM_SCAN_CASE(2); break;
@@ -442,7 +442,7 @@ static int run_scan(tm_handle *h, const uint32_t *count, uint32_t ncodes, int mo
 
 // exclusive scan of `n` counters into start[0..n] (start[n] = total); used by the point-feature kernels (tm_knn.cu)
 int exclusive_scan_u32(tm_handle *h, const uint32_t *count, uint32_t n, uint32_t *start, cudaStream_t stream) {
-    return run_scan(h, count, n, 0, start, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    return run_scan(h, count, n, 0, start, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -562,7 +562,7 @@ int build_cylinder_index(tm_handle *h, float cell_size, cudaStream_t stream) {
     TM_KCHECK(h, stream, "cyl_register_kernel (count)");
     lap("register (count)");
     align4_kernel<<<(ncodes + 255) / 256, 256, 0, stream>>>(counter, h->cyl_cell_cnt.as<uint32_t>(), rounded, ncodes);
-    int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    int rc = run_scan(h, rounded, ncodes, 0, h->cyl_cell_start.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc != TM_OK) return rc;
     uint32_t total = 0, nlong = 0;
     TM_CUDA(h, cudaMemcpyAsync(&total, h->cyl_cell_start.as<uint32_t>() + ncodes, 4, cudaMemcpyDeviceToHost, stream));
@@ -733,8 +733,7 @@ constexpr int Q_CAP = 96;             // < 32 queued pairs before a push, <= 32 
 constexpr uint32_t Q_REC = 0x80000000u;    // queue entry refers to a cylinder ROW (recA / recB) instead of a pool position
 
 struct EvalArgs {
-    const uint4 *items;
-    const uint2 *items2;
+    const uint4 *items;           // two uint4 per occupied voxel: {tile offset, near, first point, points} {far, first lane slot, -, -}
     const uint32_t *warp_item;
     unsigned int *cursor;         // next chunk of rounds the tile kernel hands out
     const float4 *sorted;
@@ -805,7 +804,9 @@ __device__ __forceinline__ uint32_t warp_append(bool want, unsigned int *counter
 constexpr int EV_BLOCKS_PER_SM = PTS_PER_LANE > 2 ? 3 : 4;
 constexpr uint32_t EV_CHUNK_ROUNDS = 4;        // consecutive rounds (groups of 32 lane slots) a warp takes per cursor fetch
 
-constexpr uint32_t EV_STAGE_CAP = 144;         // tile entries a warp stages per round: 144 x 32 B = 4.5 KB (dynamic shared memory)
+constexpr uint32_t EV_STAGE_CAP = 128;         // tile entries a warp stages per round: 128 x (32 + 4) B (dynamic shared memory;
+                                               // with the 16 KB of append staging 4 CTAs still fit an SM)
+constexpr size_t EV_STAGE_BYTES = (sizeof(float4) * 2 + sizeof(int32_t)) * EV_STAGE_CAP;      // 4608 B per warp
 
 struct __align__(16) StageScratch {           // undecided points wait here until 32 of a kind can be written with one atomic
     uint4 front[64];
@@ -815,12 +816,14 @@ struct __align__(16) StageScratch {           // undecided points wait here unti
 template <bool WIDE>
 __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kernel(EvalArgs a) {
     __shared__ StageScratch stage[EV_WARPS];
-    extern __shared__ __align__(128) unsigned char tile_stage_raw[];          // EV_WARPS x 2 x EV_STAGE_CAP float4
+    extern __shared__ __align__(128) unsigned char tile_stage_raw[];          // per warp: 2 x EV_STAGE_CAP float4 records, then EV_STAGE_CAP rows
     __shared__ __align__(8) uint64_t tile_bar[EV_WARPS];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     StageScratch &sg = stage[threadIdx.x >> 5];
-    float4 *stage_tile = reinterpret_cast<float4 *>(tile_stage_raw) + static_cast<size_t>(threadIdx.x >> 5) * 2 * EV_STAGE_CAP;
+    unsigned char *stage_base = tile_stage_raw + static_cast<size_t>(threadIdx.x >> 5) * EV_STAGE_BYTES;
+    float4 *stage_tile = reinterpret_cast<float4 *>(stage_base);
+    int32_t *stage_rows = reinterpret_cast<int32_t *>(stage_base + sizeof(float4) * 2 * EV_STAGE_CAP);
     uint64_t *bar = &tile_bar[threadIdx.x >> 5];
     uint32_t bar_phase = 0;
     if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -874,33 +877,39 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
         for (uint32_t cur = chunk * chunk_rounds; cur < r_end; ++cur) {
             // ---- which voxel run does this lane's slot belong to?  The warp's 32 slots span at most 32 consecutive items.
             const uint32_t it0 = a.warp_item[cur];
-            const uint32_t mine = it0 + lane < n_items ? a.items2[it0 + lane].y : 0xFFFFFFFFu;
+            uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0xFFFFFFFFu, 0, 0);       // lane l holds the record of item it0 + l
+            if (it0 + lane < n_items) { r0 = a.items[2 * (it0 + lane)]; r1 = a.items[2 * (it0 + lane) + 1]; }
             const uint32_t s = (cur << 5) + lane;
             const bool valid = s < total_slots;
             uint32_t lo = 0, hi = 32;
 #pragma unroll
             for (int step = 0; step < 5; ++step) {
                 const uint32_t mid = (lo + hi) >> 1;
-                const uint32_t v = __shfl_sync(0xffffffffu, mine, mid);
+                const uint32_t v = __shfl_sync(0xffffffffu, r1.y, mid);
                 if (v <= s) lo = mid; else hi = mid;
             }
-            const uint32_t slot_start = __shfl_sync(0xffffffffu, mine, lo);
+            // the lane's own item: its record sits in lane `lo` (no second trip to memory)
             const uint32_t item = it0 + lo;
-            const uint4 it = valid ? a.items[item] : make_uint4(0, 0, 0, 0);
-            const uint32_t tile_off = it.x, near_cnt = it.y;
+            const uint32_t tile_off = __shfl_sync(0xffffffffu, r0.x, lo);
+            const uint32_t near_raw = __shfl_sync(0xffffffffu, r0.y, lo), first_pt = __shfl_sync(0xffffffffu, r0.z, lo),
+                           n_pts = __shfl_sync(0xffffffffu, r0.w, lo), far_raw = __shfl_sync(0xffffffffu, r1.x, lo),
+                           slot_start = __shfl_sync(0xffffffffu, r1.y, lo);
+            const uint32_t near_cnt = valid ? near_raw : 0u;
             const uint32_t k = valid ? s - slot_start : 0u;
-            const uint32_t p0 = it.z + PTS_PER_LANE * k;
+            const uint32_t p0 = first_pt + PTS_PER_LANE * k;
             bool pv[PTS_PER_LANE];
 #pragma unroll
-            for (int q = 0; q < PTS_PER_LANE; ++q) pv[q] = valid && PTS_PER_LANE * k + q < it.w;
+            for (int q = 0; q < PTS_PER_LANE; ++q) pv[q] = valid && PTS_PER_LANE * k + q < n_pts;
             const float4 *tile = a.tileAB + 2 * static_cast<size_t>(tile_off);
             // ---- the near parts of the tiles this round touches (the warp's slots span n_dist consecutive items), staged
-            //      into the warp's shared-memory buffer with bulk asynchronous copies (TMA, one per tile, issued by the lane
-            //      that stands for the item) completing on the warp's mbarrier: one request per tile instead of one L2 round
-            //      trip per entry in the loop below.  Rounds whose tiles do not fit read them from global memory.
+            //      into the warp's shared-memory buffer with bulk asynchronous copies (TMA: records and cylinder rows of every
+            //      tile, issued by the lane that holds the item's record) completing on the warp's mbarrier: one request per
+            //      tile instead of one L2 round trip per entry in the loop below.  Tiles start on multiples of 4 entries in
+            //      the pool and in the buffer (16-byte alignment of the row indices).  Rounds whose tiles do not fit read them
+            //      from global memory.
             const uint32_t n_dist = __reduce_max_sync(0xffffffffu, valid ? lo + 1u : 0u);
-            uint32_t st_near = 0, st_off = 0;
-            if (lane < n_dist) { const uint4 di = a.items[it0 + lane]; st_off = di.x; st_near = di.y; }
+            const uint32_t st_off = r0.x;
+            const uint32_t st_near = lane < n_dist ? (r0.y + 3u) & ~3u : 0u;
             uint32_t st_pos = st_near;                                  // inclusive scan of the near lengths
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, st_pos, o); if (lane >= static_cast<uint32_t>(o)) st_pos += v; }
@@ -909,9 +918,12 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
             const bool staged = st_total > 0u && st_total <= EV_STAGE_CAP;
             if (staged) {
                 fence_proxy_async();                                    // the previous round's reads precede these writes
-                if (lane == 0) mbar_expect_tx(bar, st_total * 32u);
+                if (lane == 0) mbar_expect_tx(bar, st_total * 36u);
                 __syncwarp();
-                if (lane < n_dist && st_near) bulk_g2s(stage_tile + 2 * st_pos, a.tileAB + 2 * static_cast<size_t>(st_off), st_near * 32u, bar);
+                if (st_near) {
+                    bulk_g2s(stage_tile + 2 * st_pos, a.tileAB + 2 * static_cast<size_t>(st_off), st_near * 32u, bar);
+                    bulk_g2s(stage_rows + st_pos, a.tileI + st_off, st_near * 4u, bar);
+                }
             }
             const uint32_t my_pos = __shfl_sync(0xffffffffu, st_pos, lo);
             float4 P[PTS_PER_LANE];
@@ -968,14 +980,14 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
                 cert[q] = up[q] <= a.near;
                 const float w = d1 + 2.f * S;
                 const bool fast = pv[q] && !lists && cert[q] && tr[q].m2 > w * w;      // m2 = -1 (unreliable entry) fails
-                if (fast) a.win[__float_as_int(P[q].w)] = a.tileI[tile_off + tr[q].bj];
+                if (fast) a.win[__float_as_int(P[q].w)] = staged ? stage_rows[my_pos + tr[q].bj] : a.tileI[tile_off + tr[q].bj];
                 todo[q] = pv[q] && !fast;
                 any_todo = any_todo || todo[q];
             }
 
             if (__any_sync(0xffffffffu, any_todo)) {
                 // voxels without any tile entry (clutter far from every cylinder) and no list to run: straight to the pending list
-                const bool empty = !lists && valid && near_cnt == 0u && a.items2[item].x == 0u;
+                const bool empty = !lists && valid && near_cnt == 0u && far_raw == 0u;
 #pragma unroll
                 for (int q = 0; q < PTS_PER_LANE; ++q) {
                     const uint4 rec = make_uint4(p0 + q, item, __float_as_uint(up[q]), 0u);
@@ -1067,9 +1079,9 @@ __device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, 
             total = is_front ? d.y : d.z;
         } else {
             P = a.sorted[rec.x];
-            const uint4 it = a.items[rec.y];
+            const uint4 it = a.items[2 * rec.y];
             off = it.x;
-            total = is_front ? it.y : it.y + a.items2[rec.y].x;
+            total = is_front ? it.y : it.y + a.items[2 * rec.y + 1].x;
         }
     }
     float thr = __uint_as_float(rec.z);            // NaN without a reliable estimate: nothing is culled
@@ -1570,7 +1582,7 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     d.pts = a.pts; d.n = a.n; d.row_stride = a.row_stride;
     d.tile_desc = h->tile_desc.as<uint4>();
     EvalArgs &ev = d.ev;
-    ev.items = nullptr; ev.items2 = nullptr; ev.warp_item = nullptr; ev.cursor = nullptr; ev.sorted = nullptr;
+    ev.items = nullptr; ev.warp_item = nullptr; ev.cursor = nullptr; ev.sorted = nullptr;
     ev.tileAB = h->tileAB.as<float4>(); ev.tileI = h->tileI.as<int32_t>();
     ev.recA = h->recA.as<float4>(); ev.recB = h->recB.as<float4>();
     ev.special = h->special.as<int32_t>(); ev.aligned = h->aligned.as<int32_t>(); ev.long_list = h->long_list.as<int32_t>();
@@ -1675,8 +1687,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const int pad = n <= 3000000 ? 1 : CELL_PAD;
     TM_CUDA(h, h->cells.ensure(sizeof(uint2) * pad * nsub * (static_cast<size_t>(ncodes) + 1)));
     TM_CUDA(h, h->sorted_pts.ensure(sizeof(float4) * n));
-    TM_CUDA(h, h->items.ensure(sizeof(uint4) * (max_occ + 1)));
-    TM_CUDA(h, h->items2.ensure(sizeof(uint2) * (max_occ + 1)));
+    TM_CUDA(h, h->items.ensure(sizeof(uint4) * 2 * (max_occ + 1)));
     TM_CUDA(h, h->warp_item.ensure(sizeof(uint32_t) * max_wslots));
     TM_CUDA(h, h->undecided.ensure(sizeof(uint4) * n));
     TM_CUDA(h, h->pend_idx.ensure(sizeof(int32_t) * n));
@@ -1697,7 +1708,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     h->stats.launches += 1;
     mark(h, 1, st);
     int rc = run_scan(h, h->cells.as<uint32_t>(), ncodes, 1, h->cells.as<uint32_t>(), h->cyl_cell_start.as<uint32_t>(),
-                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(), h->items2.as<uint2>(),
+                      h->cyl_cell_cnt.as<uint32_t>(), h->cyl_cell_near.as<uint32_t>(), h->items.as<uint4>(),
                       h->warp_item.as<uint32_t>(), dst, st, nsub, pad);
     if (rc != TM_OK) return rc;
     TM_KCHECK(h, st, "scan kernels");
@@ -1710,7 +1721,6 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     mark(h, 3, st);
     EvalArgs ev;
     ev.items = h->items.as<uint4>();
-    ev.items2 = h->items2.as<uint2>();
     ev.warp_item = h->warp_item.as<uint32_t>();
     ev.cursor = cursor;
     ev.sorted = h->sorted_pts.as<float4>();
@@ -1739,7 +1749,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     const bool wide = a.prm.perp_atol > 2.f * ev.amb;
     if (guard) ev.n_aligned = 0;              // variant B never yields NaN on an axis line
     const int ev_blocks = h->sm_count * 4;
-    const size_t stage_bytes = sizeof(float4) * 2 * EV_STAGE_CAP * EV_WARPS;
+    const size_t stage_bytes = EV_STAGE_BYTES * EV_WARPS;
     if (wide) {
         TM_CUDA(h, cudaFuncSetAttribute(evaluate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
         evaluate_kernel<true><<<h->sm_count * EV_BLOCKS_PER_SM, EV_WARPS * 32, stage_bytes, st>>>(ev);
