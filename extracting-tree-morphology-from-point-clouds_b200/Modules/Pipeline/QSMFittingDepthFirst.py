@@ -42,14 +42,14 @@ def _fingerprint(points: np.ndarray) -> bytes:
 
 
 def _ensure_resident(eng: api.Engine, dev: torch.device, points: np.ndarray) -> None:
-    layout = (points.__array_interface__["data"][0], points.shape, points.strides, points.dtype.str, eng.installs_cloud)
+    layout = (points.__array_interface__["data"][0], points.shape, points.strides, points.dtype.str, eng.serial, eng.installs_cloud)
     held = _resident.get(dev.index)
     if held is not None:
         ref, held_layout, held_print = held
         if ref() is points and held_layout == layout and held_print == _fingerprint(points):
             return
     eng.upload_cloud(points[:, :3])
-    layout = layout[:-1] + (eng.installs_cloud,)
+    layout = layout[:-1] + (eng.installs_cloud,)          # the upload just bumped it
     try:
         ref = weakref.ref(points)
     except TypeError:                       # objects that cannot be weakly referenced are uploaded every time

@@ -61,6 +61,9 @@ def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else int(t.data_ptr())
 
 
+_engine_serial = 0          # every Engine gets its own number: caches keyed on "this engine's n-th install" cannot mix engines up
+
+
 class Engine:
     """One C-ABI handle (one device, one host thread)."""
 
@@ -76,6 +79,9 @@ class Engine:
         h = ctypes.c_void_p()
         B.check(self._lib, None, self._lib.tm_create(dev.index, ctypes.byref(h)))
         self._h = h
+        global _engine_serial
+        _engine_serial += 1
+        self.serial = _engine_serial
         self.m = 0
         self.installs = 0          # bumped by every set_cylinders: callers that cache "my table is installed" compare it
         self.installs_cloud = 0    # bumped by every upload_cloud: callers that cache "my cloud is resident" compare it

@@ -19,7 +19,8 @@ QSM_COLUMNS = ("startX", "startY", "startZ", "endX", "endY", "endZ", "radius", "
 # The objects are held strongly: an address can be recycled by the caching allocator the moment its tensor dies, so
 # only "the very same live tensor objects, unmodified, and nobody installed another table since" skips the install.
 _table_key: dict[int, tuple] = {}
-# device index -> ((variant, norm_fma, engine install counter), (M,7) float32 table, int32 IDs) of the last DataFrame install
+# device index -> ((variant, norm_fma, engine serial, engine install counter), (M,7) float32 table, int32 IDs) of the last
+# DataFrame install
 _frame_key: dict[int, tuple] = {}
 
 
@@ -38,7 +39,7 @@ def _same_table(dev_index: int, eng, given: tuple) -> bool:
     if held is None:
         return False
     objs, versions, installs = held
-    return (installs == eng.installs and len(objs) == len(given)
+    return (installs == (eng.serial, eng.installs) and len(objs) == len(given)
             and all(a is b for a, b in zip(objs, given))
             and all(t._version == v for t, v in zip(given, versions)))
 
@@ -66,7 +67,7 @@ def closest_cylinder(points, start, radius, axis_length, axis_unit, IDs, device,
     if not (reusable and _same_table(dev.index, eng, given)):
         eng.set_cylinders(start_t, radius_t, length_t, unit_t, ids_t)
         if reusable:
-            _table_key[dev.index] = (given, tuple(t._version for t in given), eng.installs)
+            _table_key[dev.index] = (given, tuple(t._version for t in given), (eng.serial, eng.installs))
         else:
             _table_key.pop(dev.index, None)
     m = start_t.shape[0]
@@ -100,7 +101,7 @@ def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None,
     # the same QSM again (augmented clouds of one tree, repeated calls): the table and its voxel index are still installed.
     # Decided on the VALUES (a 1.6 MB comparison at 50k cylinders), never on object identity.
     held = _frame_key.get(dev.index)
-    if not (held is not None and held[0] == (variant, norm_fma, eng.installs) and held[1].shape == table.shape
+    if not (held is not None and held[0] == (variant, norm_fma, eng.serial, eng.installs) and held[1].shape == table.shape
             and np.array_equal(held[1], table, equal_nan=True) and np.array_equal(held[2], ids_np)):
         start = torch.as_tensor(table[:, 0:3], device=dev)
         end = torch.as_tensor(table[:, 3:6], device=dev)
@@ -108,7 +109,7 @@ def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None,
         ids = torch.as_tensor(ids_np, device=dev)
         length, unit = eng.prepare(start, end, variant, norm_fma=norm_fma)
         eng.set_cylinders(start, radius, length, unit, ids)
-        _frame_key[dev.index] = ((variant, norm_fma, eng.installs), table, ids_np)
+        _frame_key[dev.index] = ((variant, norm_fma, eng.serial, eng.installs), table, ids_np)
         _table_key.pop(dev.index, None)
     cloud = np.asarray(cloud)
     if cloud.ndim != 2 or cloud.shape[1] < 3:

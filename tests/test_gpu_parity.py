@@ -713,3 +713,28 @@ def test_direct_and_sorted_paths_agree_in_fresh_processes(tmp_path):
         for k in ("index", "id", "dist", "offset"):
             a, b = outs["0"][vn][k], outs["1"][vn][k]
             assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"variant {vn}: {k} differs between the two paths"
+
+
+def test_table_caches_do_not_survive_an_engine_replacement():
+    """The drop-ins skip re-installing a table they installed before.  The key carries the engine's serial number: a NEW engine
+    whose install counter happens to match must not be taken for the one that holds the table."""
+    from treemorph_b200 import dropin, synth
+    from treemorph_b200.PreProcessing import LabelGenerationCuda as L
+    dev = torch.device("cuda", torch.cuda.current_device())
+    q1, q2 = synth.random_qsm(300, seed=61), synth.random_qsm(300, seed=62)
+    cloud = synth.sample_points(q1, 4000, seed=63).astype(np.float64)
+    df1, df2 = synth.qsm_dataframe(q1), synth.qsm_dataframe(q2)
+    want1 = _oracle.label_cloud(cloud, q1, _oracle.VARIANT_A)
+    assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df1, dev), want1, equal_nan=True)
+    old = api.get_engine(dev)
+    installs = old.installs
+    old.close()                                                           # the process-wide engine is replaced ...
+    fresh = api.get_engine(dev)
+    assert fresh is not old and fresh.serial != old.serial
+    while fresh.installs < installs:                                      # ... and brought to the same install count with ANOTHER table
+        s, r, l, u, i = synth.cylinder_arrays(q2)
+        fresh.set_cylinders(*[torch.tensor(x, device=dev) for x in (s, r, l, u)], torch.tensor(i, device=dev))
+    assert fresh.installs == installs
+    assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df1, dev), want1, equal_nan=True)
+    want2 = _oracle.label_cloud(cloud, q2, _oracle.VARIANT_A)
+    assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df2, dev), want2, equal_nan=True)
