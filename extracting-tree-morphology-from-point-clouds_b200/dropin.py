@@ -142,13 +142,13 @@ def _write_npy(path, array: np.ndarray, threads: int = 4) -> None:
     head = io.BytesIO()
     np.lib.format.write_array_header_1_0(head, np.lib.format.header_data_from_array_1_0(array))
     header = head.getvalue()
-    payload = memoryview(array).cast("B")
+    payload = memoryview(np.ascontiguousarray(array).reshape(-1).view(np.uint8))
     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
     try:
         os.write(fd, header)
         size = len(payload)
         step = max(8 << 20, -(-size // threads))
-        spans = [(lo, min(size, lo + step)) for lo in range(0, size, step)]
+        spans = [(lo, min(size, lo + step)) for lo in range(0, size, step)] or [(0, 0)]
 
         def put(span):
             lo, hi = span

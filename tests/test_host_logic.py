@@ -112,3 +112,16 @@ def test_load_cloud_las_branch_with_a_stand_in_for_laspy(tmp_path, monkeypatch, 
     monkeypatch.setattr(Utils, "laspy", _Broken)
     assert Utils.load_cloud(str(path)) is None                      # any failure: message + None, like the reference
     assert "Failed to load point cloud" in capsys.readouterr().out
+
+
+def test_threaded_npy_writer_produces_np_save_bytes(tmp_path):
+    """dropin._write_npy (the drivers' file writer: header + payload copied into the page cache by several threads) writes
+    exactly what np.save writes, for the (N,11) record, small arrays, and sizes that do not divide by the thread count."""
+    from treemorph_b200 import dropin
+    rng = np.random.default_rng(3)
+    for shape in ((0, 11), (1, 11), (1000, 11), (300_001, 11), (1_100_000, 7)):
+        a = rng.random(shape)
+        dropin._write_npy(str(tmp_path / "mine.npy"), a)
+        np.save(tmp_path / "ref.npy", a)
+        assert (tmp_path / "mine.npy").read_bytes() == (tmp_path / "ref.npy").read_bytes(), shape
+        assert np.array_equal(np.load(tmp_path / "mine.npy"), a)
