@@ -18,8 +18,9 @@ bit-identical to the single-GPU labelling (key "sharded_parity").  --scaling wea
 
 `e2e` goes through the call a user of the reference makes: LabelGenerationCuda.generate_offset_cloud_cuda_batched(
 float64 pageable cloud, DataFrame, device) -> (N,7) float64 records, table install and every copy inside the timed
-region; `e2e_pinned` is Engine.label_cloud_host on page-locked buffers with the table resident.  Prints ONE JSON line
-on rank 0.
+region; `e2e_pinned` is Engine.label_cloud_host on page-locked buffers with the table resident.  At N = 1 the line also
+carries `cpu_baseline` (the reference algorithm on the host cores, oracle port) and `reference_cuda` (the reference's ATen
+call chain on this GPU, bounded sample, results compared bit for bit).  Prints ONE JSON line on rank 0.
 
 Timing: CUDA events on the launching stream around every step, L2 flushed between steps (256 MiB write),
 barrier + synchronize on both sides of the timed loop, max over ranks.
@@ -536,7 +537,7 @@ def main():
                  "fp32_frac": bp * OPS_PER_PAIR / (bms * 1e-3) / fp32_peak if fp32_peak else None}
 
     # ---- reference algorithm on the host cores, bounded sample, same run
-    cpu = None
+    cpu = reference_cuda = None
     if not args.skip_cpu and world == 1:          # the contract: rank 0 at N = 1 only
         from oracle import oracle
         oracle.build()
@@ -546,6 +547,25 @@ def main():
         cpu = {"value": n_s / dt, "unit": UNIT, "cores": host_threads(), "kind": "port",
                "sample": f"first {n_s} points x {N_CYLINDERS} cylinders, {dt:.1f} s, OpenMP {host_threads()} threads "
                          f"of {os.cpu_count()} host cpus; ids equal to the GPU result: {same}"}
+        # the reference's own deployment is device=cuda (Modules/Utils.py:146-158): its ATen call chain, restated op for op
+        # (oracle/torch_mirror.py, checker code like the CPU port), on THIS GPU with the DataFrame table layout and the
+        # reference's batch size, on a bounded sample of the same cloud — the GPU-versus-GPU comparator
+        try:
+            from oracle import torch_mirror
+            n_r = min(len(pts_host), 20_480)
+            torch_mirror.label(pts_host[:2048], qsm, dev, 1e-6, 0.0, 0.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref = torch_mirror.label(pts_host[:n_r], qsm, dev, 1e-6, 0.0, 0.0)
+            torch.cuda.synchronize()
+            dt_r = time.perf_counter() - t0
+            reference_cuda = {"value": n_r / dt_r, "unit": UNIT, "kind": "torch mirror of the reference's ATen chain on this GPU",
+                              "sample": f"first {n_r} points x {N_CYLINDERS} cylinders, batch_size 1024, {dt_r:.2f} s",
+                              "ids_equal_to_ours": bool((ref["id"] == out["id"][:n_r].cpu().numpy()).all()),
+                              "dist_bitwise_equal_to_ours": bool(np.array_equal(ref["dist"], out["dist"][:n_r].cpu().numpy(), equal_nan=True)),
+                              "speedup_device_resident": value / (n_r / dt_r), "speedup_e2e": (e2e_value or 0.0) / (n_r / dt_r)}
+        except Exception as exc:           # e.g. out of memory on a smaller part: the comparator is optional
+            reference_cuda = {"unavailable": str(exc)[:200]}
 
     launches_per_step = stats.get("launches") or {"grid": 11, "auto": 11, "brute": 2}[args.mode]
     shard_txt = (f"ONE plot of {N_POINTS} points sharded over {world} GPU(s) ({n_mine} rows on rank 0)" if strong
@@ -571,7 +591,7 @@ def main():
                        "host_assembly_threads": pipe_pinned["host_threads"]},
         "gpu_launches": launches_per_step * steps,
         "roofline": roofline, "fp32_roofline": fp32_roofline, "step_view": step_view, "brute_force_yardstick": brute,
-        "cpu_baseline": cpu, "weak": weak, "sharded_parity": parity,
+        "cpu_baseline": cpu, "reference_cuda": reference_cuda, "weak": weak, "sharded_parity": parity,
         "phases_ms": phases, "stats": stats, "setup_ms": setup_ms, "table_broadcast_ms": bcast_ms, "table_broadcast_first_ms": first_bcast_ms, "table_broadcast": comm_note,
         "input_generation_s": gen_s,
     }
