@@ -2,17 +2,18 @@
 //
 //   per table (tm_set_cylinders + first use of a cell size):
 //     every voxel V gets a TILE: the cylinders whose capsule comes within D_max of box(V), sorted by
-//     lb(V, c) = a lower bound of dist(box(V), capsule(c)), packed contiguously (float4 A | float4 B | row | lb).
+//     lb(V, c) = a lower bound of dist(box(V), capsule(c)), packed contiguously ({float4 A, float4 B} | row | lb).
 //     The leading `near(V)` entries are those with lb <= D_near.
 //   per call:
 //     points --count/scan/scatter--> counting sort by voxel id (brick-Morton order) --> contiguous per-voxel runs
 //     evaluate:  every lane owns a (voxel, <= 2 points) slot of the sorted cloud and walks the NEAR part of its own
-//                voxel's tile (lanes of one voxel read the same 32-byte records: one L1 request), computing for every
+//                voxel's tile — the tiles a warp's 32 slots touch are staged into shared memory with bulk asynchronous
+//                copies (TMA) each round, lanes of one voxel read the same words —, computing for every
 //                entry a ~30-instruction closed-form distance ESTIMATE in cylinder-local coordinates.  When the best
 //                estimate beats the runner-up by more than twice the rounding allowance, no entry is numerically
 //                delicate, and the best is within D_near, the winner is decided without a single reference-order
 //                evaluation (the epilogue computes the winner's distance and offset in reference order anyway).
-//                The other points (~8 %: near-ties, interior points, the noise tail) take the exact path: lanes across
+//                The other points (~6 %: near-ties, interior points, the noise tail) take the exact kernel: a walk over
 //                the tile's entries in ascending lower-bound order, capsule cull against the estimate, survivors
 //                queued and evaluated 32 at a time with the reference arithmetic, 64-bit (distance, row) keys —
 //                torch.argmin's comparator.  A point whose exact best distance is <= D_near is CERTIFIED: every
