@@ -91,21 +91,22 @@ def offset_cloud(cloud, cylinders, device, variant: api.Variant, masterBar=None,
     del masterBar, batch_size
     dev = _cuda_device(device)
     eng = api.get_engine(dev)
-    # single-column access: DataFrame[[...]] re-indexes and copies through a block manager (1.5 ms per call for nothing)
-    def col(name, dtype=np.float32):
-        return np.asarray(cylinders[name].to_numpy(), dtype=dtype)
-    table = np.stack([col("startX"), col("startY"), col("startZ"), col("endX"), col("endY"), col("endZ"), col("radius")], axis=1)
+    # one (7, M) float32 block, filled column by column (DataFrame[[...]] re-indexes and copies through a block manager, and
+    # a row-major (M,7) block costs strided writes: 0.5 ms instead of 1.7 at 50k cylinders)
+    m = len(cylinders)
+    table = np.empty((7, m), dtype=np.float32)
+    for k, name in enumerate(QSM_COLUMNS[:7]):
+        table[k] = cylinders[name].to_numpy()
     ids_np = np.asarray(cylinders["ID"].to_numpy()).astype(np.int32)
-    m = table.shape[0]
     norm_fma = m <= 1                        # DataFrame tensors are Fortran-ordered in the reference (strided norm)
     # the same QSM again (augmented clouds of one tree, repeated calls): the table and its voxel index are still installed.
-    # Decided on the VALUES (a 1.6 MB comparison at 50k cylinders), never on object identity.
+    # Decided on the VALUES, bit for bit (a 1.6 MB comparison at 50k cylinders: 0.2 ms), never on object identity.
     held = _frame_key.get(dev.index)
     if not (held is not None and held[0] == (variant, norm_fma, eng.serial, eng.installs) and held[1].shape == table.shape
-            and np.array_equal(held[1], table, equal_nan=True) and np.array_equal(held[2], ids_np)):
-        start = torch.as_tensor(table[:, 0:3], device=dev)
-        end = torch.as_tensor(table[:, 3:6], device=dev)
-        radius = torch.as_tensor(table[:, 6], device=dev)
+            and np.array_equal(held[1].view(np.uint32), table.view(np.uint32)) and np.array_equal(held[2], ids_np)):
+        start = torch.as_tensor(table[0:3].T, device=dev)        # (M,3) views with strides (1, M): the reference's own layout
+        end = torch.as_tensor(table[3:6].T, device=dev)
+        radius = torch.as_tensor(table[6], device=dev)
         ids = torch.as_tensor(ids_np, device=dev)
         length, unit = eng.prepare(start, end, variant, norm_fma=norm_fma)
         eng.set_cylinders(start, radius, length, unit, ids)
