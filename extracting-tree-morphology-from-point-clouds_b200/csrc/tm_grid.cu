@@ -1087,9 +1087,10 @@ __device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, 
     }
     float thr = __uint_as_float(rec.z);            // NaN without a reliable estimate: nothing is culled
     // the walk below reads the tile entry by entry: ask for the first lines now, the rest as the walk advances
+    constexpr uint32_t AHEAD = GS > 8 ? 4u * GS : 32u;          // entries requested ahead of the walk (four steps of a wide group)
     if (total) {
         if (sub == 0) prefetch_l1(a.tileLB + off);
-        for (uint32_t e = 4 * sub; e < min(total, 32u); e += 4 * GS) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + e));
+        for (uint32_t e = 4 * sub; e < min(total, AHEAD); e += 4 * GS) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + e));
     }
     if (sub == 0) { ws.P[g] = P; ws.best[g] = KEY_NONE; }
     __syncwarp();
@@ -1100,8 +1101,8 @@ __device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, 
         bool hit = false;
         float lb = INF;
         if (!cut && j < total) {
-            if ((j & 3u) == 0u && j + 32u < total) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + j + 32u));
-            if ((j & 31u) == 0u && j + 64u < total) prefetch_l1(a.tileLB + off + j + 64u);
+            if ((j & 3u) == 0u && j + AHEAD < total) prefetch_l1(a.tileAB + 2 * static_cast<size_t>(off + j + AHEAD));
+            if ((j & 31u) == 0u && j + 2u * AHEAD < total) prefetch_l1(a.tileLB + off + j + 2u * AHEAD);
             lb = a.tileLB[off + j];
         }
         // the group's first entry of this step beyond the incumbent: everything from here on is farther
@@ -1179,8 +1180,12 @@ __device__ __forceinline__ void exact_task(const EvalArgs &a, ExactScratch &ws, 
     __syncwarp();                    // ws.P / ws.best are rewritten by the next task
 }
 
+// Lanes per point of a walk: a walk is a chain of dependent steps, so a small call (every warp gets a task or two anyway)
+// spends more lanes on each point and finishes in fewer steps; a large one is throughput work, one lane per point.
 constexpr int EXACT_FAR_LANES = 8;
-constexpr uint32_t EXACT_FAR_WIDE_BELOW = 100000;       // far walks use 8 lanes per point while there are few of them (latency), 1 beyond (throughput)
+constexpr uint32_t EXACT_FAR_WIDE_BELOW = 100000;       // far walks (hundreds of entries): 8 lanes per point below this many of them,
+constexpr uint32_t EXACT_FAR_WARP_BELOW = 4096;         //   a whole warp per point below this
+constexpr uint32_t EXACT_NEAR_WIDE_BELOW = 131072;      // near walks (tens of entries): 8 lanes per point below this many
 
 template <bool GUARD, bool NFMA, bool DIRECT>
 __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
@@ -1189,18 +1194,22 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
     const uint32_t lt = (1u << lane) - 1u;
     ExactScratch &ws = scratch[warp];
     const uint32_t n_front = a.st->undecided_near, n_back = a.st->undecided_far;
-    const bool wide_far = n_back < EXACT_FAR_WIDE_BELOW;                       // grid-uniform
-    const uint32_t PB = wide_far ? 32u / EXACT_FAR_LANES : 32u;
-    const uint32_t w_front = (n_front + 31u) >> 5, w_all = w_front + (n_back + PB - 1u) / PB;
+    // grid-uniform choices
+    const uint32_t far_lanes = n_back < EXACT_FAR_WARP_BELOW ? 32u : (n_back < EXACT_FAR_WIDE_BELOW ? static_cast<uint32_t>(EXACT_FAR_LANES) : 1u);
+    const uint32_t near_lanes = n_front < EXACT_NEAR_WIDE_BELOW ? static_cast<uint32_t>(EXACT_FAR_LANES) : 1u;
+    const uint32_t PB = 32u / far_lanes, PF = 32u / near_lanes;
+    const uint32_t w_front = (n_front + PF - 1u) / PF, w_all = w_front + (n_back + PB - 1u) / PB;
     unsigned int pairs = 0, culls = 0, nfar = 0;
     uint32_t qn = 0;
     // the long walks first: they are the critical path of a small call
     for (uint32_t w = blockIdx.x * EV_WARPS + warp; w < w_all; w += gridDim.x * EV_WARPS) {
         if (w < w_all - w_front) {
-            if (wide_far) exact_task<GUARD, NFMA, DIRECT, EXACT_FAR_LANES>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
-            else exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
+            if (far_lanes == 32u) exact_task<GUARD, NFMA, DIRECT, 32>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
+            else if (far_lanes == 1u) exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
+            else exact_task<GUARD, NFMA, DIRECT, EXACT_FAR_LANES>(a, ws, lane, lt, w, false, n_back, qn, pairs, culls, nfar);
         } else {
-            exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w - (w_all - w_front), true, n_front, qn, pairs, culls, nfar);
+            if (near_lanes == 1u) exact_task<GUARD, NFMA, DIRECT, 1>(a, ws, lane, lt, w - (w_all - w_front), true, n_front, qn, pairs, culls, nfar);
+            else exact_task<GUARD, NFMA, DIRECT, EXACT_FAR_LANES>(a, ws, lane, lt, w - (w_all - w_front), true, n_front, qn, pairs, culls, nfar);
         }
     }
     unsigned long long all_culls = culls;
@@ -1225,6 +1234,7 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int DIRECT_THREADS = 256;
 constexpr uint32_t DIRECT_BINS = 64;          // near lengths 0..62 get their own bin, longer ones share the last
+constexpr uint32_t DIRECT_AHEAD = 16;         // tile entries requested ahead of the estimate loop (4 lines of 128 bytes)
 
 struct DirectArgs {
     const float *pts;
@@ -1270,6 +1280,13 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 6) direct_kernel(DirectArgs a,
             code = point_code(g, x, y, z);
             if (code != NO_CELL) desc = a.tile_desc[code];
             bin = min(desc.y, DIRECT_BINS - 1u);
+            // the estimate loop below reads the tile entry by entry, one dependent trip to memory each (a cold table: HBM
+            // latency x the longest near part of the block); ask for the first lines now, while the block is being ordered
+            // (tiles start on 128-byte lines of 4 entries), the rest as the loop advances
+            if (desc.y) {
+                prefetch_l1(e.tileI + desc.x);
+                for (uint32_t k = 0; k < min(desc.y, DIRECT_AHEAD); k += 4) prefetch_l1(e.tileAB + 2 * static_cast<size_t>(desc.x + k));
+            }
         }
         rank = atomicAdd(&s_hist[bin], 1u);
         __syncthreads();
@@ -1302,6 +1319,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 6) direct_kernel(DirectArgs a,
         float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
         if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
         for (uint32_t j = 0; j < max_near; j += 2) {
+            if ((j & 2u) == 0u && j + DIRECT_AHEAD < near_cnt) prefetch_l1(tile + 2 * (j + DIRECT_AHEAD));
             if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
             if (j < near_cnt) bound_pair<WIDE>(P.x, P.y, P.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t0);
             if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
@@ -1552,8 +1570,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32) ring_kernel(RingArgs a, GridD
 // ------------------------------------------------------------------------------------------------
 // Small clouds take the direct path: the sorted path pays ~0.1 ms per call that does not depend on the number of points
 // (scan over every voxel of the grid, a dozen launches), the direct path pays ~0.25 us per 1000 points for its uncoalesced
-// tile reads.  Measured crossover on a randomly ordered cloud against 50k cylinders: ~800k points
-// (profiles/r02_floor_phases.json); TM_DIRECT=0/1 forces either.
+// tile reads.  Measured crossover on a randomly ordered cloud against 50k cylinders: ~500k points
+// (profiles/r02_floor_direct_vs_sorted.json); TM_DIRECT=0/1 forces either.
 static bool overlap_enabled() {
     static const bool on = [] { const char *e = getenv("TM_OVERLAP"); return !(e && e[0] == '0'); }();
     return on;
@@ -1562,7 +1580,7 @@ static bool overlap_enabled() {
 static bool use_direct(const tm_handle *, const LabelArgs &a) {
     static const int forced = [] { const char *e = getenv("TM_DIRECT"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced != 0;
-    return a.n <= 600000;
+    return a.n <= 500000;
 }
 
 static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, float slack) {

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "floor.json"))
     ap.add_argument("--cylinders", type=int, default=50_000)
     ap.add_argument("--sizes", default="10000,100000,1000000,1250000,2500000,5000000,10000000")
+    ap.add_argument("--cells", default="0", help="comma-separated voxel edges to try (0 = the library's own choice)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     eng = api.Engine(dev)
@@ -36,18 +37,18 @@ def main():
                       torch.tensor(unit, device=dev), torch.tensor(ids, device=dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
-    for n in sizes:
+    for n, cell in [(n, float(c)) for n in sizes for c in args.cells.split(",")]:
         p = pts[:n]
         out = {"index": torch.empty(n, dtype=torch.int32, device=dev), "id": torch.empty(n, dtype=torch.int32, device=dev),
                "dist": torch.empty(n, dtype=torch.float32, device=dev), "offset": torch.empty((n, 3), dtype=torch.float32, device=dev)}
         for _ in range(3):
-            eng.label(p, api.VARIANT_A, mode="grid", out=out)
+            eng.label(p, api.VARIANT_A, mode="grid", cell_size=cell, out=out)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
         torch.cuda.synchronize()
         for a, b in evs:
             flush.fill_(1)
             a.record()
-            eng.label(p, api.VARIANT_A, mode="grid", out=out)
+            eng.label(p, api.VARIANT_A, mode="grid", cell_size=cell, out=out)
             b.record()
         torch.cuda.synchronize()
         ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
@@ -55,11 +56,11 @@ def main():
         acc = {}
         for _ in range(5):
             flush.fill_(1)
-            eng.label(p, api.VARIANT_A, mode="grid", out=out)
+            eng.label(p, api.VARIANT_A, mode="grid", cell_size=cell, out=out)
             for k, v in eng.phase_ms().items():
                 acc.setdefault(k, []).append(v)
         eng.set_profiling(False)
-        row = {"points": n, "cylinders": args.cylinders, "ms": ms, "points_per_s": n / (ms * 1e-3),
+        row = {"points": n, "cylinders": args.cylinders, "cell": cell, "ms": ms, "points_per_s": n / (ms * 1e-3),
                "phases_ms": {k: round(float(np.median(v)), 4) for k, v in acc.items()}}
         rows.append(row)
         print(json.dumps(row), flush=True)
