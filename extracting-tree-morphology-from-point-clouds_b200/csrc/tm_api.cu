@@ -575,7 +575,13 @@ static int label_cloud_host_assemble(tm_handle *h, const void *cloud_host, int32
     }
     cudaStream_t s_in = h->pipe_stream[0], s_cmp = h->pipe_stream[1], s_out = h->pipe_stream[2], s_rows = h->pipe_stream[3];
     h->host_assembly_threads = static_cast<int32_t>(nthreads);
-    int64_t chunk = 1 << 20;
+    // About four chunks per call: every chunk costs the calling thread ~0.15 ms of fixed work (a dozen launches, two copies,
+    // two hand-offs to the worker pool), and with fewer than three the copies no longer hide behind the host's passes
+    // (10M points: 20 chunks 15.2 ms, 10 chunks 13.2, 5 chunks 12.4, 3 chunks 12.2, 2 chunks 14.0 —
+    // profiles/r02_e2e_chunks.json).  Bounded below (small clouds: the fixed work) and above (page-locked staging: 32 bytes
+    // per point and slot).
+    int64_t chunk = std::min<int64_t>(std::max<int64_t>((n + 3) / 4, 512 << 10), 2560 << 10);
+    chunk = (chunk + 4095) & ~static_cast<int64_t>(4095);
     if (const char *env = getenv("TM_HOST_CHUNK")) { const long long v = atoll(env); if (v >= 1024) chunk = v; }
     chunk = std::min(chunk, n);
     int depth = tmn::PIPE_SLOTS;
