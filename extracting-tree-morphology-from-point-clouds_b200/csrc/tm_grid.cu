@@ -33,6 +33,7 @@
 // allowance), so the argmin and its lowest-index tie-break are those of the exhaustive search.  Cylinders that cannot
 // be bounded (non-finite, non-unit axis) are evaluated for every point; axis-parallel cylinders get the exact
 // on-axis-line test in variant A (NaN wins the argmin at any distance).
+#include <array>
 #include <algorithm>
 #include <cmath>
 #include <chrono>
@@ -756,6 +757,7 @@ struct EvalArgs {
     const float *pts;
     int64_t row_stride;
     const uint4 *tile_desc;       // per voxel code {tile offset, near length, tile length, 0}
+    uint32_t far_warp_below, far_wide_below, near_wide_below;     // exact kernel: lanes per walk by list length (see EXACT_*)
 };
 
 struct Track {                    // per point: smallest and second smallest squared estimate, entry of the smallest
@@ -1195,8 +1197,8 @@ __global__ void __launch_bounds__(EV_WARPS * 32, 4) exact_kernel(EvalArgs a) {
     ExactScratch &ws = scratch[warp];
     const uint32_t n_front = a.st->undecided_near, n_back = a.st->undecided_far;
     // grid-uniform choices
-    const uint32_t far_lanes = n_back < EXACT_FAR_WARP_BELOW ? 32u : (n_back < EXACT_FAR_WIDE_BELOW ? static_cast<uint32_t>(EXACT_FAR_LANES) : 1u);
-    const uint32_t near_lanes = n_front < EXACT_NEAR_WIDE_BELOW ? static_cast<uint32_t>(EXACT_FAR_LANES) : 1u;
+    const uint32_t far_lanes = n_back < a.far_warp_below ? 32u : (n_back < a.far_wide_below ? static_cast<uint32_t>(EXACT_FAR_LANES) : 1u);
+    const uint32_t near_lanes = n_front < a.near_wide_below ? static_cast<uint32_t>(EXACT_FAR_LANES) : 1u;
     const uint32_t PB = 32u / far_lanes, PF = 32u / near_lanes;
     const uint32_t w_front = (n_front + PF - 1u) / PF, w_all = w_front + (n_back + PB - 1u) / PB;
     unsigned int pairs = 0, culls = 0, nfar = 0;
@@ -1577,6 +1579,20 @@ static bool overlap_enabled() {
     return on;
 }
 
+// TM_EXACT_LANES="far_warp,far_wide,near_wide" overrides the list lengths below which the exact kernel spends 32 / 8 / 8
+// lanes on a walk (experiments)
+static void exact_lane_thresholds(EvalArgs &ev) {
+    static const std::array<uint32_t, 3> v = [] {
+        std::array<uint32_t, 3> t{EXACT_FAR_WARP_BELOW, EXACT_FAR_WIDE_BELOW, EXACT_NEAR_WIDE_BELOW};
+        if (const char *e = getenv("TM_EXACT_LANES")) {
+            unsigned a = 0, b = 0, c = 0;
+            if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) t = {a, b, c};
+        }
+        return t;
+    }();
+    ev.far_warp_below = v[0]; ev.far_wide_below = v[1]; ev.near_wide_below = v[2];
+}
+
 static bool use_direct(const tm_handle *, const LabelArgs &a) {
     static const int forced = [] { const char *e = getenv("TM_DIRECT"); return e ? atoi(e) : -1; }();
     if (forced >= 0) return forced != 0;
@@ -1619,6 +1635,7 @@ static int label_direct(tm_handle *h, const LabelArgs &a, const GridDev &g, floa
     ev.pend_keys = h->keys.as<unsigned long long>();
     ev.st = dst;
     ev.pts = a.pts; ev.row_stride = a.row_stride; ev.tile_desc = h->tile_desc.as<uint4>();
+    exact_lane_thresholds(ev);
     d.recAB = h->recAB.as<float4>();
     d.ids = h->ids.as<int32_t>();
     d.move_to_mantle = a.prm.move_to_mantle;
@@ -1764,6 +1781,7 @@ int label_grid(tm_handle *h, const LabelArgs &a) {
     ev.pend_keys = h->keys.as<unsigned long long>();
     ev.st = dst;
     ev.pts = a.pts; ev.row_stride = a.row_stride; ev.tile_desc = h->tile_desc.as<uint4>();
+    exact_lane_thresholds(ev);
     const bool guard = a.prm.norm_eps > 0.f, nfma = a.prm.norm_fma != 0;
     const bool wide = a.prm.perp_atol > 2.f * ev.amb;
     if (guard) ev.n_aligned = 0;              // variant B never yields NaN on an axis line
