@@ -738,3 +738,47 @@ def test_table_caches_do_not_survive_an_engine_replacement():
     assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df1, dev), want1, equal_nan=True)
     want2 = _oracle.label_cloud(cloud, q2, _oracle.VARIANT_A)
     assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df2, dev), want2, equal_nan=True)
+
+
+def test_dataframe_layouts_and_edits_reach_the_kernel():
+    """The drop-in reads the QSM columns by name into one float32 block and re-installs the table only when that block
+    differs bit for bit from the installed one: column order, extra columns and the frame's dtypes must not matter, an edited
+    value (also a NaN that appears or a zero that changes sign) must."""
+    from treemorph_b200 import synth
+    from treemorph_b200.PreProcessing import LabelGenerationCuda as L
+    dev = torch.device("cuda", torch.cuda.current_device())
+    q = synth.random_qsm(400, seed=71)
+    cloud = synth.sample_points(q, 5000, seed=72).astype(np.float64)
+    df = synth.qsm_dataframe(q)
+    want = _oracle.label_cloud(cloud, q, _oracle.VARIANT_A)
+    eng = api.get_engine(dev)
+    assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df, dev), want, equal_nan=True)
+    installs = eng.installs
+    # same values, another frame object: float32 columns in another order, extra columns, integer IDs as int64
+    cols = list(df.columns)[::-1]
+    other = df[cols].copy()
+    for c in ("startX", "startY", "startZ", "endX", "endY", "endZ", "radius"):
+        other[c] = other[c].astype(np.float32)
+    other["ID"] = other["ID"].astype(np.int64)
+    other["note"] = "x"
+    other.insert(0, "volume", 1.0)
+    assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, other, dev), want, equal_nan=True)
+    assert eng.installs == installs                                        # recognised by value: not installed again
+    # one radius edited in place in the caller's frame
+    edited = df.copy()
+    edited.loc[edited.index[7], "radius"] *= 3.0
+    q_edit = dict(q)
+    q_edit["radius"] = np.array(q["radius"], dtype=np.float64, copy=True)
+    q_edit["radius"][7] *= 3.0
+    got = L.generate_offset_cloud_cuda_batched(cloud, edited, dev)
+    assert eng.installs == installs + 1
+    assert np.array_equal(got, _oracle.label_cloud(cloud, q_edit, _oracle.VARIANT_A), equal_nan=True)
+    # a NaN row: installed once, recognised on the second call (NaN compares equal to itself bit for bit)
+    broken = df.copy()
+    broken.loc[broken.index[3], "endX"] = np.nan
+    first = L.generate_offset_cloud_cuda_batched(cloud, broken, dev)
+    count = eng.installs
+    again = L.generate_offset_cloud_cuda_batched(cloud, broken.copy(), dev)
+    assert eng.installs == count and np.array_equal(first, again, equal_nan=True)
+    # and back to the original table
+    assert np.array_equal(L.generate_offset_cloud_cuda_batched(cloud, df, dev), want, equal_nan=True)
