@@ -937,29 +937,26 @@ __global__ void __launch_bounds__(EV_WARPS * 32, EV_BLOCKS_PER_SM) evaluate_kern
             Track tr[PTS_PER_LANE];
 #pragma unroll
             for (int q = 0; q < PTS_PER_LANE; ++q) tr[q] = Track{INF, INF, 0u};
-            const uint32_t max_near = __reduce_max_sync(0xffffffffu, near_cnt);
             if (staged) {
                 mbar_wait(bar, bar_phase);
                 bar_phase ^= 1u;
                 const float4 *mine_tile = stage_tile + 2 * my_pos;         // lanes of one voxel read the same words: broadcast
+                // every lane runs over its own tile's length (lanes of one voxel stay together, the others leave the loop
+                // early): no per-entry reconvergence bookkeeping
 #pragma unroll 2
-                for (uint32_t j = 0; j < max_near; ++j) {
-                    if (j < near_cnt) {
-                        const float4 A = mine_tile[2 * j], B = mine_tile[2 * j + 1];
+                for (uint32_t j = 0; j < near_cnt; ++j) {
+                    const float4 A = mine_tile[2 * j], B = mine_tile[2 * j + 1];
 #pragma unroll
-                        for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A, B, band_lo, band_hi, S, rho2_min, j, tr[q]);
-                    }
+                    for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A, B, band_lo, band_hi, S, rho2_min, j, tr[q]);
                 }
                 __syncwarp();                                               // everyone is done with the buffer
             } else {
                 float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
                 if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
-                for (uint32_t j = 0; j < max_near; j += 2) {
+                for (uint32_t j = 0; j < near_cnt; j += 2) {
                     if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
-                    if (j < near_cnt) {
 #pragma unroll
-                        for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A0, B0, band_lo, band_hi, S, rho2_min, j, tr[q]);
-                    }
+                    for (int q = 0; q < PTS_PER_LANE; ++q) bound_pair<WIDE>(P[q].x, P[q].y, P[q].z, A0, B0, band_lo, band_hi, S, rho2_min, j, tr[q]);
                     if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
                     if (j + 1u < near_cnt) {
 #pragma unroll
@@ -1317,13 +1314,12 @@ __global__ void __launch_bounds__(DIRECT_THREADS, 6) direct_kernel(DirectArgs a,
 
         Track t0{INF, INF, 0u};
         const float4 *tile = e.tileAB + 2 * static_cast<size_t>(tile_off);
-        const uint32_t max_near = __reduce_max_sync(0xffffffffu, near_cnt);
         float4 A0 = make_float4(0.f, 0.f, 0.f, 0.f), B0 = A0, A1 = A0, B1 = A0;
         if (0u < near_cnt) { A0 = tile[0]; B0 = tile[1]; }
-        for (uint32_t j = 0; j < max_near; j += 2) {
+        for (uint32_t j = 0; j < near_cnt; j += 2) {               // per-lane trip count: the lanes meet again after the loop
             if ((j & 2u) == 0u && j + DIRECT_AHEAD < near_cnt) prefetch_l1(tile + 2 * (j + DIRECT_AHEAD));
             if (j + 1u < near_cnt) { A1 = tile[2 * (j + 1u)]; B1 = tile[2 * (j + 1u) + 1]; }
-            if (j < near_cnt) bound_pair<WIDE>(P.x, P.y, P.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t0);
+            bound_pair<WIDE>(P.x, P.y, P.z, A0, B0, band_lo, band_hi, S, rho2_min, j, t0);
             if (j + 2u < near_cnt) { A0 = tile[2 * (j + 2u)]; B0 = tile[2 * (j + 2u) + 1]; }
             if (j + 1u < near_cnt) bound_pair<WIDE>(P.x, P.y, P.z, A1, B1, band_lo, band_hi, S, rho2_min, j + 1u, t0);
         }
