@@ -89,7 +89,9 @@ struct DevStats {
 
 // FP32 lane-operations of one closed-form distance estimate of the tile kernel (tm_grid.cu: bound_pair), counted the way
 // SURVEY.md A.6 counts the reference's 81: every add / sub / mul / fma / min / max / compare / select / rsqrt is one
-constexpr uint32_t LANE_OPS_PER_BOUND = 33;
+// (variant A as compiled: 10 FFMA + 4 FADD + 2 FMUL + 1 MUFU + 4 FSETP + 4 FMNMX + 1 FMNMX3 + 2 FSEL + 1 SEL per estimate in the
+// SASS of the staged loop; variant B has one compare and one select more)
+constexpr uint32_t LANE_OPS_PER_BOUND = 29;
 
 struct HostPool;                     // tm_api.cu
 

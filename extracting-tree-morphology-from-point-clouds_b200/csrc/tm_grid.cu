@@ -772,20 +772,20 @@ __device__ __forceinline__ void bound_pair(float px, float py, float pz, const f
                                            float band_hi, float S, float rho2_min, uint32_t j, Track &tr) {
     const float vx = px - A.x, vy = py - A.y, vz = pz - A.z;
     const float t = fmaf(vz, B.z, fmaf(vy, B.y, vx * B.x));
-    const float tc = fminf(fmaxf(t, 0.f), A.w);
-    const float d = t - tc;
+    const float ad = fmaxf(fmaxf(-t, t - A.w), 0.f);         // |t - clamp(t, 0, L)|: one subtraction and one 3-input max (FMNMX3)
     const float rx = fmaf(-t, B.x, vx), ry = fmaf(-t, B.y, vy), rz = fmaf(-t, B.z, vz);     // rejection from the axis LINE
     const float rho2 = fmaf(rz, rz, fmaf(ry, ry, fmaf(rx, rx, 1e-30f)));       // + 1e-30: rsqrt stays finite on the axis line
     const float rho = rho2 * mufu_rsq(rho2);
     const float a = rho - B.w;
-    const float ad = fabsf(d);
     const bool beyond = ad > band_hi;                       // certainly not perp
     const bool undecided = WIDE ? (!beyond && ad >= band_lo) : !beyond;
-    const float asel = beyond ? fmaxf(a, 0.f) : a;
+    // inside the slab the form keeps the sign of a; without the certain band (!WIDE) every slab entry with a < S is
+    // unreliable anyway, so max(a, 0) serves both cases there
+    const float asel = WIDE ? (beyond ? fmaxf(a, 0.f) : a) : fmaxf(a, 0.f);
     const bool unrel = (undecided && a < S) || rho2 < rho2_min;
     // an unreliable entry gives no upper bound either (variant B divides by max(rho, 1e-8): with rho below the guard the
     // foot point collapses towards the axis and the distance grows to sqrt(d^2 + r^2)): it only forces the exact path
-    const float D = unrel ? __int_as_float(0x7f800000) : fmaf(asel, asel, d * d);
+    const float D = unrel ? __int_as_float(0x7f800000) : fmaf(asel, asel, ad * ad);
     tr.m2 = fminf(tr.m2, fmaxf(tr.m1, D));
     tr.bj = D < tr.m1 ? j : tr.bj;
     tr.m1 = fminf(tr.m1, D);
